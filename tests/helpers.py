@@ -1,0 +1,120 @@
+"""Shared test helpers: seeded weights / inputs that need neither the reference nor a GPU.
+
+Everything here is generated with numpy's PCG64 (stable across numpy versions), so the golden generator (run in
+the build container against /root/reference) and the GPU box (no reference) see bit-identical weights/inputs.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+DEPTH = {"uit_xs": 12, "uit_xxs": 6, "uit_xxxs": 4}
+ARCHS = ("uit_xs", "uit_xxs", "uit_xxxs")
+OUTPUTDIM = 537
+
+
+def _t(a) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: int = OUTPUTDIM,
+                    grid_t: int = 6) -> Dict[str, torch.Tensor]:
+    """A full UiT state_dict (same keys/shapes/dtypes as the reference).
+
+    kind='init'    ~ the reference's default init statistics (flat outputs, BN = identity).
+    kind='trained' ~ weights with trained-like scale so that no branch is trivially identity and the 537
+                     probabilities spread over (0, 1) (top-5 comparisons become meaningful).
+    """
+    from oracle import uit_oracle as O     # only for the analytic window / mel filterbank buffers
+    depth = DEPTH[arch]
+    g = np.random.Generator(np.random.PCG64([seed, depth, 0 if kind == "init" else 1]))
+    tr = kind == "trained"
+
+    def lin(out_f, in_f, std):
+        return _t(g.standard_normal((out_f, in_f)) * std)
+
+    def vec(n, mean, std):
+        return _t(mean + g.standard_normal(n) * std)
+
+    D, H, I = 128, 384, 32
+    sd: Dict[str, torch.Tensor] = {}
+    sd["cls_token"] = _t(g.standard_normal((1, 1, D)) * 1e-6)
+    sd["token_pos_embed"] = _t(g.standard_normal((1, D)) * 0.02)
+    sd["time_pos_embed"] = _t(g.standard_normal((1, D, 1, grid_t)) * (0.3 if tr else 0.02))
+    sd["freq_pos_embed"] = _t(g.standard_normal((1, D, 4, 1)) * (0.3 if tr else 0.02))
+    sd["front_end.0.spectrogram.window"] = O.hann_window()
+    sd["front_end.0.mel_scale.fb"] = O.melscale_fbanks_htk()
+    sd["init_bn.1.weight"] = vec(64, 1.0, 0.1 if tr else 0.0)
+    sd["init_bn.1.bias"] = vec(64, 0.0, 0.1 if tr else 0.0)
+    sd["init_bn.1.running_mean"] = vec(64, 5.0 if tr else 0.0, 5.0 if tr else 0.0)
+    sd["init_bn.1.running_var"] = _t(g.uniform(50.0, 200.0, 64)) if tr else torch.ones(64)
+    sd["init_bn.1.num_batches_tracked"] = torch.tensor(1234 if tr else 0, dtype=torch.int64)
+    sd["patch_embed.proj.weight"] = _t(g.standard_normal((D, 1, 16, 16)) * (1.0 / 16.0))
+    sd["patch_embed.proj.bias"] = vec(D, 0.0, 0.05)
+    for i in range(depth):
+        p = f"blocks.{i}."
+        sd[p + "norm1.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
+        sd[p + "norm1.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+        sd[p + "attn.qkv.weight"] = lin(3 * I, D, 0.09 if tr else 0.02)
+        sd[p + "attn.qkv.bias"] = vec(3 * I, 0.0, 0.05 if tr else 0.0)
+        sd[p + "attn.proj.weight"] = lin(D, I, 0.12 if tr else 0.02)
+        sd[p + "attn.proj.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+        sd[p + "norm2.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
+        sd[p + "norm2.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+        sd[p + "mlp.fc1.weight"] = lin(H, D, 0.09 if tr else 0.02)
+        sd[p + "mlp.fc1.bias"] = vec(H, 0.0, 0.05 if tr else 0.0)
+        sd[p + "mlp.fc2.weight"] = lin(D, H, 0.04 if tr else 0.02)
+        sd[p + "mlp.fc2.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+    sd["norm.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
+    sd["norm.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+    sd["outputlayer.0.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
+    sd["outputlayer.0.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
+    sd["outputlayer.1.weight"] = lin(outputdim, D, 0.25 if tr else 0.02)
+    sd["outputlayer.1.bias"] = vec(outputdim, -1.0 if tr else 0.0, 1.0 if tr else 0.0)
+    return sd
+
+
+def noise_clips(B: int, L: int = 16000, seed: int = 1234, amp: float = 0.1) -> np.ndarray:
+    """The synthetic workload of SURVEY §8d: amp*randn clamped to [-1, 1], float32."""
+    g = np.random.Generator(np.random.PCG64([seed, L]))
+    return np.clip(g.standard_normal((B, L), dtype=np.float32) * np.float32(amp), -1.0, 1.0)
+
+
+def adversarial_batch(L: int = 16000) -> np.ndarray:
+    """zeros / full-scale sine / single impulse / loud noise / very quiet noise in ONE batch: exercises the
+    batch-global top-dB cutoff (Q2) and the amin clamp."""
+    t = np.arange(L, dtype=np.float64)
+    x = np.zeros((5, L), dtype=np.float32)
+    x[1] = np.sin(2 * np.pi * 440.0 * t / 16000.0).astype(np.float32)
+    x[2, L // 2] = 1.0
+    x[3] = noise_clips(1, L, seed=7, amp=0.9)[0]
+    x[4] = noise_clips(1, L, seed=8, amp=1e-4)[0]
+    return x
+
+
+def load_golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name))
+
+
+def samples_int16() -> np.ndarray:
+    """The reference's 11 sample clips (int16), zero-padded to 16384, plus their true lengths."""
+    z = load_golden("samples_int16.npz")
+    return z["pcm"], z["length"], [str(s) for s in z["names"]]
+
+
+def tie_aware_topk_equal(ref: np.ndarray, got: np.ndarray, k: int = 5, eps: float = 1e-3) -> bool:
+    """top-k label sets agree up to substitutions among classes whose REFERENCE probability lies within
+    2*eps of the reference k-th value (SURVEY §7.2 tolerance statement)."""
+    for r, o in zip(ref, got):
+        kth = np.sort(r)[-k]
+        must = set(np.nonzero(r > kth + 2 * eps)[0])
+        may = set(np.nonzero(r >= kth - 2 * eps)[0])
+        top = set(np.argsort(-o, kind="stable")[:k])
+        if not (must <= top and top <= may):
+            return False
+    return True

@@ -1,0 +1,97 @@
+"""The oracle against the committed golden vectors of the REAL reference (tests/golden/generate_golden.py).
+CPU only; this is what pins the checker that the GPU parity tests rely on."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_f64 as O64
+from oracle import uit_oracle as O
+from tests import helpers as H
+
+
+def _inputs():
+    pcm, length, _ = H.samples_int16()
+    x16 = np.zeros((len(pcm), 16000), np.float32)
+    for i in range(len(pcm)):
+        n = min(16000, int(length[i]))
+        x16[i, :n] = pcm[i, :n].astype(np.float32) / 32768.0
+    return {
+        "samples16k": x16, "noise": H.noise_clips(32), "adversarial": H.adversarial_batch(),
+        "short2400": H.noise_clips(3, 2400, seed=11), "short14336": H.noise_clips(3, 14336, seed=12),
+        "len16160": H.noise_clips(2, 16160, seed=14), "long10s": H.noise_clips(2, 160000, seed=13),
+    }
+
+
+INPUTS = _inputs()
+
+
+def test_buffers_match_layout_file():
+    sd = H.make_state_dict("uit_xs")
+    want = [l.rstrip("\n").split("\t") for l in open(H.GOLDEN_DIR + "/state_dict_layout.txt")]
+    want = [(k, s, d) for a, k, s, d in want if a == "uit_xs"]
+    got = [(k, str(tuple(v.shape)), str(v.dtype)) for k, v in sd.items()]
+    assert got == want
+    assert len(got) == 163
+
+
+@pytest.mark.parametrize("name", ["samples16k", "noise", "adversarial", "short2400", "short14336", "len16160", "long10s"])
+def test_logmel_bit_exact_vs_reference(name):
+    g = H.load_golden("logmel.npz")[name]
+    sd = H.make_state_dict("uit_xxxs")
+    x = torch.from_numpy(INPUTS[name])
+    db = O.logmel(x, sd["front_end.0.spectrogram.window"], sd["front_end.0.mel_scale.fb"]).numpy()
+    np.testing.assert_array_equal(db[: g.shape[0]], g)
+
+
+def test_frame_counts():
+    # SURVEY §8a2 [probed]
+    assert [O.num_frames(L) for L in (16000, 16384, 14336, 160000, 2400)] == [101, 103, 90, 1001, 16]
+    assert O.crop_starts(1001, 102) == [0, 102, 204, 306, 408, 510, 612, 714, 816, 899]
+    assert O.crop_starts(103, 102) == [0, 1]
+    assert O.crop_starts(204, 102) == [0, 102]
+    assert O.crop_starts(102, 102) == [0]
+
+
+def test_f64_restatement_agrees_on_natural_audio():
+    sd = H.make_state_dict("uit_xxxs")
+    w, fb = sd["front_end.0.spectrogram.window"].numpy(), sd["front_end.0.mel_scale.fb"].numpy()
+    for name in ("noise", "short2400"):
+        g = H.load_golden("logmel.npz")[name]
+        d = O64.logmel(INPUTS[name], w, fb)
+        assert np.abs(d - g).max() <= 1e-4 * np.abs(g).max()
+
+
+def test_q2_batch_global_cutoff():
+    """A silent clip batched with a loud one is clamped at (batch max - 120 dB), not at -100 dB."""
+    g = H.load_golden("logmel.npz")["adversarial"]
+    assert g[0].max() == g[0].min() == np.float32(g.max() - 120.0)
+
+
+@pytest.mark.parametrize("arch", H.ARCHS)
+@pytest.mark.parametrize("kind", ["init", "trained"])
+def test_forward_vs_reference(arch, kind):
+    g = H.load_golden("probs.npz")
+    sd = H.make_state_dict(arch, kind)
+    for name, x in INPUTS.items():
+        y = O.forward(sd, torch.from_numpy(x)).numpy()
+        np.testing.assert_allclose(y, g[f"{arch}/{kind}/{name}"], atol=2e-6, rtol=0)
+    pcm, length, _ = H.samples_int16()
+    nat = np.stack([O.forward(sd, torch.from_numpy(pcm[i, :length[i]].astype(np.float32)[None] / 32768.0)).numpy()[0]
+                    for i in range(len(pcm))])
+    np.testing.assert_allclose(nat, g[f"{arch}/{kind}/samples_native"], atol=2e-6, rtol=0)
+    if kind == "trained":
+        y = O.forward(sd, torch.from_numpy(INPUTS["long10s"]), eval_avg="max").numpy()
+        np.testing.assert_allclose(y, g[f"{arch}/{kind}/long10s_max"], atol=2e-6, rtol=0)
+
+
+def test_trained_weights_spread_probabilities():
+    g = H.load_golden("probs.npz")["uit_xs/trained/noise"]
+    assert g.min() < 0.05 and g.max() > 0.9
+
+
+def test_trace_matches():
+    z = H.load_golden("trace_xxxs.npz")
+    sd = H.make_state_dict("uit_xxxs", "trained")
+    tr = O.forward_trace(sd, torch.from_numpy(INPUTS["noise"][:2]))
+    for k in ("db", "bn", "tokens", "blocks", "features", "probs"):
+        np.testing.assert_allclose(tr[k].numpy(), z[k], atol=2e-5, rtol=0)
