@@ -1,0 +1,128 @@
+/*
+ * uitk.h — C ABI of the B200 (sm_100a) UiT inference kernels.
+ *
+ * The reference (RicherMans/UIT_Mobile) is pure Python and has no native/FFI interface; its extension point is
+ * the `models` package name lookup + the nn.Module protocol (models/__init__.py:1-2, models/uit.py:252-493).
+ * This library is what the Python mirror of that module (`uit_mobile_b200/models/uit.py`) binds with ctypes.
+ * Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are marked `d_`, host pointers `h_`.
+ *   - returns 0 (UITK_OK) or a negative UITK_E* code; `uitk_last_error()` gives a thread-local message.
+ *   - never allocates device memory, never synchronises, never frees: the caller owns all buffers, passes a
+ *     workspace and the CUDA stream (`cudaStream_t` as void*) to launch on, and keeps buffers alive until
+ *     the stream has passed the launch.  Re-entrant across streams/threads.
+ *   - all tensors are dense row-major fp32 unless stated.
+ */
+#ifndef UITK_H_
+#define UITK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define UITK_API __attribute__((visibility("default")))
+#else
+#define UITK_API
+#endif
+
+#define UITK_VERSION 100
+
+#define UITK_OK 0
+#define UITK_EINVAL (-1)    /* bad shape / argument */
+#define UITK_EALIGN (-2)    /* misaligned pointer */
+#define UITK_ECUDA (-3)     /* CUDA runtime error (message holds cudaGetErrorString) */
+#define UITK_EARCH (-4)     /* device is not sm_100 */
+#define UITK_ENOSPACE (-5)  /* workspace / blob too small */
+
+/* Fixed geometry of the hot path (models/uit.py:287-308, 581-635). */
+#define UITK_N_FFT 512
+#define UITK_HOP 160
+#define UITK_N_MELS 64
+#define UITK_N_FREQS 257
+#define UITK_EMBED 128
+#define UITK_PATCH 16
+#define UITK_MAX_TOKENS 24
+#define UITK_INNER 32
+#define UITK_HIDDEN 384
+
+/* Encoder arithmetic. */
+#define UITK_PREC_FP32 0   /* fp32 CUDA-core GEMMs (validation path) */
+#define UITK_PREC_BF16 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/residual/LN/softmax */
+
+UITK_API int uitk_version(void);
+UITK_API const char* uitk_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (monotonic; for bench accounting). */
+UITK_API uint64_t uitk_kernel_launches(void);
+
+/* Number of STFT frames for a clip of L samples: 1 + L/160 (torch.stft center=True). */
+UITK_API int64_t uitk_num_frames(int64_t L);
+
+/* Number of eval crops and tokens per crop for T frames (models/uit.py:468-481, 43-74). */
+UITK_API int uitk_num_crops(int64_t T, int target_length);
+UITK_API int uitk_tokens_per_crop(int64_t T, int target_length);
+
+/* ---- front-end constants -------------------------------------------------------------------------------
+ * Packs the module's persistent buffers `front_end.0.spectrogram.window[512]` and
+ * `front_end.0.mel_scale.fb[257,64]` (state_dict entries, Q9) plus FFT twiddles into the device layout of the
+ * log-mel kernel.  Host -> host; the caller uploads the blob.  Call with h_blob == NULL to get the size. */
+UITK_API size_t uitk_frontend_blob_bytes(const float* h_fb);
+UITK_API int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, size_t blob_bytes);
+
+/* ---- log-mel front-end ------------------------------------------------------------------------------------
+ * Replaces front_end = MelSpectrogram(16 kHz, n_fft 512, win 512, hop 160, 64 mels, center, reflect, power 2)
+ * -> AmplitudeToDB('power') WITHOUT the top-dB clamp (models/uit.py:298-308, 455; torchaudio
+ * functional.spectrogram / MelScale / amplitude_to_DB).
+ *   d_wav      [B, L] fp32, row stride ld_wav elements (ld_wav < L gives overlapping sliding windows)
+ *   d_db       [B, 64, T] fp32, T = 1 + L/160: 10*log10(max(mel, 1e-10)), NOT yet clamped
+ *   d_max_pow  one uint32 = bit pattern of the running max mel POWER (non-negative float, so unsigned
+ *              order == float order).  Caller zero-initialises; the kernel atomically maxes into it.
+ *              The reference's single batch-global cutoff (Q2) is max_db - 120 with
+ *              max_db = 10*log10(max(max_pow, 1e-10)); it is applied by uitk_clamp_db / uitk_encoder, after
+ *              the caller has had the chance to all-reduce(max) the word across GPUs. */
+UITK_API int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const void* d_frontend_blob,
+                float* d_db, uint32_t* d_max_pow, void* stream);
+
+/* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120). */
+UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream);
+
+/* ---- encoder weights ----------------------------------------------------------------------------------------
+ * Packs state_dict tensors (host fp32, reference layout) into the kernels' device layout.
+ * `h_tensors` is an array of host pointers in the fixed order documented in uitk_encoder_tensor_names().
+ * Host -> host; the caller uploads the blob. */
+typedef struct {
+  int depth;          /* 12 / 6 / 4 */
+  int outputdim;      /* 537 */
+  int grid_t;         /* time_pos_embed length (6 for target_length 102) */
+  int precision;      /* UITK_PREC_* */
+} uitk_encoder_cfg;
+
+UITK_API int uitk_encoder_num_tensors(int depth);
+UITK_API const char* uitk_encoder_tensor_name(int depth, int index);   /* state_dict key of h_tensors[index] */
+UITK_API size_t uitk_encoder_blob_bytes(const uitk_encoder_cfg* cfg);
+UITK_API int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* h_tensors, void* h_blob, size_t blob_bytes);
+
+/* ---- encoder ----------------------------------------------------------------------------------------------------
+ * Replaces init_bn + crop loop + forward_features + forward_head (models/uit.py:460-492, 379-412, 89-122,
+ * 181-248) for pooling='mean', BNeckAttention, ReLU MLP.
+ *   d_db        [B, 64, T] un-clamped dB from uitk_logmel; the clamp with *d_max_pow is fused into the load
+ *   d_probs     [B, outputdim] sigmoid scores, crops reduced by mean (eval_avg 0) or max (1)
+ *   workspace   uitk_encoder_workspace_bytes(cfg, B, T, target_length) bytes, 256-B aligned */
+UITK_API size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length);
+UITK_API int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
+                 int target_length, int eval_avg, const uint32_t* d_max_pow, float* d_probs,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Debug/validation taps (tests only): copy of the token activations [B*crops*tokens, 128] after patch embed
+ * (stage 0) or after block i (stage i+1) is left in the workspace at this byte offset after uitk_encoder. */
+UITK_API size_t uitk_encoder_tokens_offset(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UITK_H_ */

@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> ctypes -> C ABI -> sm_100a kernels) against
+(a) the committed golden vectors of the real reference and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances
+  log-mel (fp32):  |d| <= 1e-4 * max|ref|  (north_star "1e-4 relative"), or -- for ill-conditioned bins such as
+                   the leakage floor of a pure sine, where the reference's own fp32 FFT noise is 6e-2 dB -- the
+                   power is within 4e-6 of the frame's peak mel power of the float64 restatement (the reference
+                   itself sits at 1.1e-6 by that measure).
+  scores, fp32 encoder: |d prob| <= 5e-5.
+  scores, bf16 tensor-core encoder: |d prob| <= 5e-3 ('trained' weights) / 1e-3 ('init'), tie-aware top-5 equal.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_f64 as O64
+from oracle import uit_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _inputs():
+    pcm, length, _ = H.samples_int16()
+    x16 = np.zeros((len(pcm), 16000), np.float32)
+    for i in range(len(pcm)):
+        n = min(16000, int(length[i]))
+        x16[i, :n] = pcm[i, :n].astype(np.float32) / 32768.0
+    return {
+        "samples16k": x16, "noise": H.noise_clips(32), "adversarial": H.adversarial_batch(),
+        "short2400": H.noise_clips(3, 2400, seed=11), "short14336": H.noise_clips(3, 14336, seed=12),
+        "len16160": H.noise_clips(2, 16160, seed=14), "long10s": H.noise_clips(2, 160000, seed=13),
+    }
+
+
+INPUTS = _inputs()
+_MODELS = {}
+
+
+def model(arch, kind="trained", precision="fp32", **kw):
+    import uit_mobile_b200 as U
+    key = (arch, kind, precision, tuple(sorted(kw.items())))
+    if key not in _MODELS:
+        m = getattr(U.models, arch)(outputdim=537, target_length=102, precision=precision, **kw)
+        m.load_state_dict(H.make_state_dict(arch, kind), strict=True)
+        _MODELS[key] = m.to(DEV).eval()
+    return _MODELS[key]
+
+
+def assert_logmel_close(got, x, ref32):
+    sd = H.make_state_dict("uit_xxxs")
+    w, fb = sd["front_end.0.spectrogram.window"].numpy(), sd["front_end.0.mel_scale.fb"].numpy()
+    ok = np.abs(got - ref32) <= 1e-4 * np.abs(ref32).max()
+    if not ok.all():
+        mel = O64.mel_power(x, w, fb)
+        gmax = 10 * np.log10(max(mel.max(), 1e-10))
+        p64 = np.maximum(np.maximum(mel, 1e-10), 10 ** ((gmax - 120) / 10))
+        pg = 10 ** (got.astype(np.float64) / 10)
+        ok |= np.abs(pg - p64) <= 4e-6 * p64.max(axis=1, keepdims=True)
+    bad = np.argwhere(~ok)
+    assert ok.all(), f"{len(bad)} log-mel values out of tolerance, first {bad[:3]}, max |d| {np.abs(got - ref32).max()}"
+
+
+def test_library_loaded_is_in_tree():
+    from uit_mobile_b200 import _native as N
+    assert N.lib().uitk_version() == 100
+    assert N.LIB_PATH.endswith("uit_mobile_b200/libuitk.so")
+
+
+@pytest.mark.parametrize("name", list(INPUTS))
+def test_logmel_vs_reference_golden(name):
+    m = model("uit_xxxs")
+    x = INPUTS[name]
+    ref = H.load_golden("logmel.npz")[name]
+    got = m.front_end(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    n = ref.shape[0]            # the long10s golden keeps clip 0 only (noise never reaches the clamp)
+    got, x = got[:n], x[:n]
+    assert got.shape == ref.shape
+    assert_logmel_close(got, x, ref)
+    if name == "noise":
+        assert np.abs(got - ref).max() <= 2e-4          # typical: a few 1e-5 dB
+
+
+def test_logmel_q2_batch_global_cutoff():
+    m = model("uit_xxxs")
+    got = m.front_end(torch.from_numpy(INPUTS["adversarial"]).to(DEV)).cpu().numpy()
+    ref = H.load_golden("logmel.npz")["adversarial"]
+    assert got[0].min() == got[0].max()
+    assert abs(float(got[0].max()) - float(ref[0].max())) <= 1e-4
+    assert abs(float(got.max() - got.min()) - 120.0) <= 1e-4
+
+
+def test_logmel_sliding_windows_strided_view():
+    """Windows of a long stream are read in place (row stride = hop), no [W,16000] copy (BASELINE config 5)."""
+    m = model("uit_xxxs")
+    stream = torch.from_numpy(H.noise_clips(1, 16000 * 6, seed=21)[0]).to(DEV)
+    hop = 1600
+    W = (stream.numel() - 16000) // hop + 1
+    view = stream.as_strided((W, 16000), (hop, 1))
+    db_v, mp_v = m.front_end.logmel_unclamped(stream, ld=hop, B=W, L=16000)
+    db_c, mp_c = m.front_end.logmel_unclamped(view.contiguous())
+    assert torch.equal(db_v, db_c) and torch.equal(mp_v, mp_c)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_fp32_encoder_block_trace(depth):
+    """Token activations after block `depth` vs the reference trace (a depth-truncated model is packed)."""
+    import uit_mobile_b200 as U
+    z = H.load_golden("trace_xxxs.npz")
+    sd = H.make_state_dict("uit_xxxs", "trained")
+    sub = {k: v for k, v in sd.items() if not k.startswith("blocks.") or int(k.split(".")[1]) < depth}
+    m = U.models.UITBase(outputdim=537, target_length=102, patch_size=16, embed_dim=128, depth=depth, num_heads=2,
+                         mlp_ratio=3.0, pooling="mean", init_bn=True, act_layer=torch.nn.ReLU,
+                         attention_type="BNeckAttention")
+    m.load_state_dict(sub, strict=True)
+    m = m.to(DEV).eval()
+    x = torch.from_numpy(INPUTS["noise"][:2]).to(DEV)
+    m(x)
+    torch.cuda.synchronize()
+    tok = m._last_workspace[: 2 * 24 * 128 * 4].view(torch.float32).view(2, 24, 128).cpu().numpy()
+    np.testing.assert_allclose(tok, z["blocks"][depth - 1], atol=2e-4, rtol=0)
+
+
+@pytest.mark.parametrize("arch", H.ARCHS)
+@pytest.mark.parametrize("kind", ["init", "trained"])
+def test_fp32_scores_vs_reference_golden(arch, kind):
+    g = H.load_golden("probs.npz")
+    m = model(arch, kind)
+    worst = 0.0
+    for name, x in INPUTS.items():
+        y = m(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        ref = g[f"{arch}/{kind}/{name}"]
+        assert y.shape == ref.shape == (x.shape[0], 537)
+        worst = max(worst, float(np.abs(y - ref).max()))
+        assert H.tie_aware_topk_equal(ref, y, 5, eps=5e-5)
+    assert worst <= 5e-5, worst
+
+
+@pytest.mark.parametrize("arch", ["uit_xs", "uit_xxxs"])
+def test_fp32_native_length_samples_two_crop_branch(arch):
+    """inference.py feeds whole files: the 16 384-sample water_*.wav take the 2-crop branch (T=103)."""
+    g = H.load_golden("probs.npz")[f"{arch}/trained/samples_native"]
+    pcm, length, _ = H.samples_int16()
+    m = model(arch)
+    for i in range(len(pcm)):
+        x = torch.from_numpy(pcm[i, : length[i]].astype(np.float32)[None] / 32768.0).to(DEV)
+        y = m(x).cpu().numpy()[0]
+        assert np.abs(y - g[i]).max() <= 5e-5
+
+
+def test_fp32_eval_avg_max_ten_crops():
+    g = H.load_golden("probs.npz")["uit_xxs/trained/long10s_max"]
+    m = model("uit_xxs", eval_avg="max")
+    y = m(torch.from_numpy(INPUTS["long10s"]).to(DEV)).cpu().numpy()
+    assert np.abs(y - g).max() <= 5e-5
+
+
+def test_fp32_vs_oracle_large_seeded_batch():
+    """Same seeded inputs through the oracle (CPU) and the CUDA path at a size the oracle finishes in seconds."""
+    x = H.noise_clips(512, seed=99)
+    sd = H.make_state_dict("uit_xs", "trained")
+    ref = O.forward(sd, torch.from_numpy(x)).numpy()
+    y = model("uit_xs")(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert np.abs(y - ref).max() <= 5e-5
+    assert H.tie_aware_topk_equal(ref, y, 5, eps=5e-5)
+
+
+def test_shard_invariance_single_gpu():
+    """Two half-batches that share the all-reduced max word reproduce the full-batch scores bit for bit."""
+    m = model("uit_xxs")
+    x = torch.from_numpy(INPUTS["adversarial"]).to(DEV)
+    full = m(x)
+    a, b = x[:2].contiguous(), x[2:].contiguous()
+    db_a, mp_a = m.front_end.logmel_unclamped(a)
+    db_b, mp_b = m.front_end.logmel_unclamped(b)
+    mp = torch.maximum(mp_a, mp_b)
+    y = torch.cat([m.encode(db_a, mp), m.encode(db_b, mp)])
+    assert torch.equal(full, y)
+
+
+def test_batch_chunking_is_invisible():
+    m = model("uit_xxxs")
+    x = torch.from_numpy(H.noise_clips(70, seed=5)).to(DEV)
+    full = m(x)
+    old = m.max_clips_per_launch
+    try:
+        m.max_clips_per_launch = 16
+        assert torch.equal(full, m(x))
+    finally:
+        m.max_clips_per_launch = old
+
+
+def test_errors_are_loud():
+    from uit_mobile_b200 import _native as N
+    m = model("uit_xxxs")
+    with pytest.raises(N.UitkError):
+        m(torch.zeros(2, 16000))                       # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        m(torch.zeros(16000, device=DEV))              # 1-D input (reference raises in einops, Q8)
+    with pytest.raises(N.UitkError):
+        m(torch.zeros(2, 2000, device=DEV))            # < 16 frames
+    with pytest.raises(N.UitkError):
+        m(torch.zeros(2, 16000, device=DEV, dtype=torch.float64))
+    m.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            m(torch.zeros(2, 16000, device=DEV))
+    finally:
+        m.eval()

@@ -1,0 +1,136 @@
+"""CPU-only tests of the boundary: the C-ABI library loads and exports every symbol include/uitk.h declares,
+the host-side packers produce the documented layouts, and the Python mirror keeps the reference's module
+contract.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uit_oracle as O
+from tests import helpers as H
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from uit_mobile_b200 import build
+    from uit_mobile_b200 import _native as N
+    build.build()
+    return N.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from uit_mobile_b200 import _native as N
+    hdr = open(os.path.join(H.REPO, "include", "uitk.h")).read()
+    declared = set(re.findall(r"UITK_API\s+[\w\s\*]+?\b(uitk_\w+)\s*\(", hdr))
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.uitk_version() == 100
+
+
+def test_geometry_helpers_match_oracle(lib):
+    for L in (2400, 14336, 16000, 16160, 16384, 160000):
+        T = O.num_frames(L)
+        assert lib.uitk_num_frames(L) == T
+        assert lib.uitk_num_crops(T, 102) == len(O.crop_starts(T, 102))
+        tc = min(T, 102)
+        assert lib.uitk_tokens_per_crop(T, 102) == 4 * ((tc - 16) // 16 + 1)
+
+
+def test_frontend_pack_layout(lib):
+    win, fb = O.hann_window(), O.melscale_fbanks_htk()
+    n = lib.uitk_frontend_blob_bytes(fb.data_ptr())
+    blob = np.zeros(n, np.uint8)
+    assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, n) == 0
+    i32, f32 = blob.view(np.int32), blob.view(np.float32)
+    assert i32[0] == 0x55464531 and i32[1] == 500            # SURVEY: 500 non-zeros [probed]
+    np.testing.assert_array_equal(f32[4:516], win.numpy())
+    tw256 = f32[516:516 + 512].reshape(256, 2)
+    j = np.arange(256)
+    np.testing.assert_allclose(tw256[:, 0] + 1j * tw256[:, 1], np.exp(-2j * np.pi * j / 256), atol=1e-7)
+    base = 516 + 1024
+    lo, cnt, off = i32[base:base + 64], i32[base + 64:base + 128], i32[base + 128:base + 192]
+    w = f32[base + 192:]
+    dense = np.zeros((257, 64), np.float32)
+    for m in range(64):
+        dense[lo[m]:lo[m] + cnt[m], m] = w[off[m]:off[m] + cnt[m]]
+    np.testing.assert_array_equal(dense, fb.numpy())
+    # error path: blob too small
+    assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, 16) == -5
+    assert b"needs" in lib.uitk_last_error()
+
+
+def test_encoder_pack_tensor_order_and_size(lib):
+    from uit_mobile_b200 import _native as N
+    names = N.encoder_tensor_names(4)
+    sd = H.make_state_dict("uit_xxxs")
+    assert len(names) == 14 + 12 * 4 and all(n in sd for n in names)
+    dead = set(sd) - set(names)
+    assert dead == {"cls_token", "token_pos_embed", "front_end.0.spectrogram.window", "front_end.0.mel_scale.fb",
+                    "init_bn.1.num_batches_tracked"}
+    cfg = N.EncoderCfg(4, 537, 6, 0)
+    assert lib.uitk_encoder_blob_bytes(C.byref(cfg)) > 4 * 568089 * 0.9
+    bad = N.EncoderCfg(4, 5000, 6, 0)
+    assert lib.uitk_encoder_blob_bytes(C.byref(bad)) == 0 and b"outputdim" in lib.uitk_last_error()
+
+
+def test_launch_entry_points_validate_before_touching_cuda(lib):
+    assert lib.uitk_logmel(None, 1, 16000, 16000, None, None, None, None) == -1
+    one = C.c_float(0)
+    p = C.addressof(one)
+    assert lib.uitk_logmel(p, 1, 100, 100, p, p, p, None) == -1 and b"reflect" in lib.uitk_last_error()
+
+
+def test_module_contract():
+    import uit_mobile_b200 as U
+    assert set(U.models.PRETRAINED_CHECKPOINTS) == {"uit_xs", "uit_xxs", "uit_xxxs"}
+    for arch in H.ARCHS:
+        m = getattr(U.models, arch)(**U.models.PRETRAINED_CHECKPOINTS[arch]["model_kwargs"])
+        want = [l.rstrip("\n").split("\t")[1:] for l in open(H.GOLDEN_DIR + "/state_dict_layout.txt") if l.startswith(arch + "\t")]
+        got = [[k, str(tuple(v.shape)), str(v.dtype)] for k, v in m.state_dict().items()]
+        assert got == want
+        m.load_state_dict(H.make_state_dict(arch), strict=True)
+        assert m.target_length == 102 and m.hop_size == 160 and m.n_mels == 64 and m.outputdim == 537
+        assert m.patch_embed.grid_size == (4, 6) and m.pooling == "mean" and m.eval_avg == "mean"
+        assert m.no_weight_decay() == {"time_pos_embed", "cls_token", "freq_pos_embed", "token_pos_embed"}
+        assert sum(p.numel() for p in m.parameters()) == {"uit_xs": 1495577, "uit_xxs": 799961, "uit_xxxs": 568089}[arch]
+
+
+def test_pos_embed_resize_on_load():
+    import uit_mobile_b200 as U
+    sd = H.make_state_dict("uit_xxxs", grid_t=6)
+    m = U.models.uit_xxxs(outputdim=537, target_length=64)          # 4 time patches: slice
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.time_pos_embed, sd["time_pos_embed"][..., :4])
+    sd3 = H.make_state_dict("uit_xxxs", grid_t=3)
+    m = U.models.uit_xxxs(outputdim=537, target_length=102)         # 3 -> 6: bilinear, like uit.py:433-438
+    m.load_state_dict(sd3, strict=True)
+    want = torch.nn.functional.interpolate(sd3["time_pos_embed"], size=(1, 6), align_corners=False, mode="bilinear")
+    assert torch.equal(m.time_pos_embed, want)
+
+
+def test_unsupported_configurations_raise():
+    import uit_mobile_b200 as U
+    with pytest.raises(NotImplementedError):
+        U.models.UITBase()                                            # reference defaults: 768-dim token-pooled ViT
+    with pytest.raises(NotImplementedError):
+        U.models.uit_xs(pooling="token")
+    with pytest.raises(NotImplementedError):
+        U.models.uit_xs(n_mels=80)
+    with pytest.raises(NotImplementedError):
+        U.models.uit_xs(target_length=1012)
+
+
+def test_no_cpu_fallback():
+    import uit_mobile_b200 as U
+    from uit_mobile_b200 import _native as N
+    m = U.models.uit_xxxs(outputdim=537, target_length=102).eval()
+    with pytest.raises(N.UitkError):
+        m(torch.zeros(1, 16000))
+    with pytest.raises(RuntimeError):
+        m.blocks(torch.zeros(1, 24, 128))
+    src = open(os.path.join(H.REPO, "uit_mobile_b200", "models", "uit.py")).read()
+    assert "oracle" not in src.replace("no CPU path", "")

@@ -1,0 +1,75 @@
+"""ctypes binding of libuitk.so — the only way the Python host layer reaches the GPU kernels.
+
+There is NO fallback: if the library is missing or a call fails, a ``UitkError`` is raised.  The signatures mirror
+``include/uitk.h`` one to one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libuitk.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+class UitkError(RuntimeError):
+    pass
+
+
+class EncoderCfg(C.Structure):
+    _fields_ = [("depth", C.c_int), ("outputdim", C.c_int), ("grid_t", C.c_int), ("precision", C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/uitk.h
+SIGNATURES = {
+    "uitk_version": (C.c_int, []),
+    "uitk_last_error": (C.c_char_p, []),
+    "uitk_kernel_launches": (C.c_uint64, []),
+    "uitk_num_frames": (C.c_int64, [C.c_int64]),
+    "uitk_num_crops": (C.c_int, [C.c_int64, C.c_int]),
+    "uitk_tokens_per_crop": (C.c_int, [C.c_int64, C.c_int]),
+    "uitk_frontend_blob_bytes": (C.c_size_t, [C.c_void_p]),
+    "uitk_pack_frontend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "uitk_logmel": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uitk_clamp_db": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p]),
+    "uitk_encoder_num_tensors": (C.c_int, [C.c_int]),
+    "uitk_encoder_tensor_name": (C.c_char_p, [C.c_int, C.c_int]),
+    "uitk_encoder_blob_bytes": (C.c_size_t, [C.POINTER(EncoderCfg)]),
+    "uitk_pack_encoder": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]),
+    "uitk_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
+    "uitk_encoder": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uitk_encoder_tokens_offset": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load libuitk.so (built in-tree by ``python -m uit_mobile_b200.build``).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UitkError(f"{LIB_PATH} not found: build it with `python -m uit_mobile_b200.build` "
+                            "(there is no CPU or PyTorch fallback for the UiT hot path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().uitk_last_error()
+        raise UitkError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")
+
+
+def encoder_tensor_names(depth: int):
+    l = lib()
+    return [l.uitk_encoder_tensor_name(depth, i).decode() for i in range(l.uitk_encoder_num_tensors(depth))]

@@ -1,0 +1,91 @@
+// C ABI entry points that launch kernels (see include/uitk.h).  No allocation, no synchronisation.
+#include "uitk_common.cuh"
+
+using namespace uitk;
+
+namespace {
+
+int check_arch() {
+  static thread_local int ok_dev = -1;
+  int dev = 0;
+  UITK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev == ok_dev) return UITK_OK;
+  int major = 0;
+  UITK_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  UITK_REQUIRE(major == 10, UITK_EARCH, "libuitk is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+  ok_dev = dev;
+  return UITK_OK;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const void* d_frontend_blob, float* d_db,
+                uint32_t* d_max_pow, void* stream) {
+  UITK_REQUIRE(d_wav && d_frontend_blob && d_db && d_max_pow, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
+  UITK_REQUIRE(L > UITK_N_FFT / 2, UITK_EINVAL, "reflect padding needs L > 256 samples (got %lld)", (long long)L);
+  UITK_REQUIRE(L < (1ll << 31) * (int64_t)UITK_HOP / 2, UITK_EINVAL, "clip too long");
+  UITK_REQUIRE(ld_wav >= 1, UITK_EINVAL, "ld_wav must be >= 1");
+  UITK_REQUIRE(aligned(d_wav, 4) && aligned(d_db, 4) && aligned(d_max_pow, 4) && aligned(d_frontend_blob, 16), UITK_EALIGN,
+               "misaligned pointer");
+  if (B == 0) return UITK_OK;
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return launch_logmel(d_wav, B, L, ld_wav, reinterpret_cast<const FrontendBlob*>(d_frontend_blob), d_db, d_max_pow,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream) {
+  UITK_REQUIRE(d_db && d_max_pow, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(n >= 0, UITK_EINVAL, "negative size");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return launch_clamp_db(d_db, n, d_max_pow, top_db, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int encoder_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length, int64_t* rows) {
+  UITK_REQUIRE(cfg, UITK_EINVAL, "null cfg");
+  UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
+  UITK_REQUIRE(target_length >= 16 && target_length <= 16 * cfg->grid_t + 15, UITK_EINVAL,
+               "target_length %d incompatible with time_pos_embed length %d", target_length, cfg->grid_t);
+  UITK_REQUIRE(T >= 16, UITK_EINVAL, "need at least 16 frames (2400 samples) for one patch, got %lld", (long long)T);
+  *rows = B * crops_for(T, target_length) * 4 * time_patches_for(T, target_length);
+  return UITK_OK;
+}
+
+size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
+  int64_t rows = 0;
+  if (encoder_geometry(cfg, B, T, target_length, &rows) != UITK_OK) return 0;
+  return encoder_fp32_workspace_bytes(rows) + 256;
+}
+
+size_t uitk_encoder_tokens_offset(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
+  (void)cfg; (void)B; (void)T; (void)target_length;
+  return 0;   // x[rows][128] is the first workspace region in both precisions
+}
+
+int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
+                 int target_length, int eval_avg, const uint32_t* d_max_pow, float* d_probs, void* d_workspace,
+                 size_t workspace_bytes, void* stream) {
+  UITK_REQUIRE(cfg && d_encoder_blob && d_db && d_max_pow && d_probs && d_workspace, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(eval_avg == 0 || eval_avg == 1, UITK_EINVAL, "eval_avg must be 0 (mean) or 1 (max)");
+  UITK_REQUIRE(aligned(d_workspace, 256) && aligned(d_encoder_blob, 256) && aligned(d_db, 4) && aligned(d_probs, 4), UITK_EALIGN,
+               "misaligned pointer (workspace and blob need 256-byte alignment)");
+  int64_t rows = 0;
+  int rc = encoder_geometry(cfg, B, T, target_length, &rows);
+  if (rc != UITK_OK) return rc;
+  if (B == 0) return UITK_OK;
+  rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  EncoderArgs a{cfg, d_encoder_blob, d_db, B, T, target_length, eval_avg, d_max_pow, d_probs,
+                d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream)};
+  if (cfg->precision == UITK_PREC_FP32) return run_encoder_fp32(a);
+  set_error("precision %d not built into this library", cfg->precision);
+  return UITK_EINVAL;
+}
+
+}  // extern "C"

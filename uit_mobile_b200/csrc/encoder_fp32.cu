@@ -1,0 +1,370 @@
+// fp32 CUDA-core encoder (UITK_PREC_FP32): the exact-arithmetic validation path of the UiT encoder.
+//
+// Unfused on purpose: every stage is a small kernel whose output can be compared with the oracle, and the
+// tensor-core path (encoder_tc.cu) is checked against it on the device.  Stages (models/uit.py):
+//   patch GEMM  = top-dB clamp + eval BatchNorm (460-462) + Conv2d 16x16/16 as [rows,256]x[256,128] + pos (380-388)
+//   per block   = LN1+qkv GEMM | attention (89-122) | proj GEMM + residual | LN2+fc1 GEMM+ReLU | fc2 GEMM + residual
+//   head        = final LN(1e-6), token mean, LN(1e-5), Linear 128->outputdim, sigmoid, crop mean/max (395-404, 468-488)
+#include "uitk_common.cuh"
+
+namespace uitk {
+
+namespace {
+
+enum { PRO_PLAIN = 0, PRO_LN = 1, PRO_PATCH = 2 };
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESID = 2, EPI_PATCH = 3 };
+
+struct GemmParams {
+  const float* A; int lda;
+  const float* Wt; int ldw;
+  const float* bias;
+  float* C; int ldc;
+  int M, K;
+  // PRO_LN
+  const float* ln_w; const float* ln_b; float ln_eps;
+  // PRO_PATCH / EPI_PATCH
+  const float* db; int T; int crops; int tokens; int t_n; int target;
+  const float* bn_scale; const float* bn_shift; const uint32_t* max_pow;
+  const float* time_pos; const float* freq_pos;
+};
+
+constexpr int BM = 128, KS = 32, AS_LD = 36;
+
+template <int BN, int PRO, int EPI>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
+  constexpr int TN = BN / 16;
+  __shared__ __align__(16) float As[BM * AS_LD];
+  __shared__ __align__(16) float Ws[KS * BN];
+  __shared__ float s_mean[BM], s_rstd[BM];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (PRO == PRO_LN) {   // K == 128: one float4 per lane
+    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+      const int row = row0 + r;
+      float mean = 0.f, rstd = 0.f;
+      if (row < p.M) {
+        const float4 x = *reinterpret_cast<const float4*>(p.A + (size_t)row * p.lda + lane * 4);
+        float s = x.x + x.y + x.z + x.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean = s * (1.f / 128.f);
+        const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
+        float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd = rsqrtf(q * (1.f / 128.f) + p.ln_eps);
+      }
+      if (lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+    }
+  }
+  float cutoff = 0.f;
+  if (PRO == PRO_PATCH) cutoff = 10.f * log10f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += KS) {
+    __syncthreads();
+    // ---- A slab [128][32]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 256 * q;
+      const int r = idx >> 3, c4 = idx & 7;
+      const int row = row0 + r;
+      const int k = k0 + c4 * 4;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.M) {
+        if (PRO == PRO_PATCH) {
+          const int rr = row / p.tokens, tok = row - rr * p.tokens;
+          const int b = rr / p.crops, c = rr - b * p.crops;
+          int start = 0;
+          if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
+          const int f = tok / p.t_n, tau = tok - f * p.t_n;
+          const int mel = f * 16 + (k >> 4);
+          const int t = start + tau * 16 + (k & 15);
+          const float* src = p.db + ((size_t)b * 64 + mel) * p.T + t;
+          const float sc = p.bn_scale[mel], sh = p.bn_shift[mel];
+          val.x = fmaf(fmaxf(__ldg(src + 0), cutoff), sc, sh);
+          val.y = fmaf(fmaxf(__ldg(src + 1), cutoff), sc, sh);
+          val.z = fmaf(fmaxf(__ldg(src + 2), cutoff), sc, sh);
+          val.w = fmaf(fmaxf(__ldg(src + 3), cutoff), sc, sh);
+        } else {
+          val = *reinterpret_cast<const float4*>(p.A + (size_t)row * p.lda + k);
+          if (PRO == PRO_LN) {
+            const float mean = s_mean[r], rstd = s_rstd[r];
+            const float4 g = *reinterpret_cast<const float4*>(p.ln_w + k);
+            const float4 be = *reinterpret_cast<const float4*>(p.ln_b + k);
+            val.x = (val.x - mean) * rstd * g.x + be.x;
+            val.y = (val.y - mean) * rstd * g.y + be.y;
+            val.z = (val.z - mean) * rstd * g.z + be.z;
+            val.w = (val.w - mean) * rstd * g.w + be.w;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&As[r * AS_LD + c4 * 4]) = val;
+    }
+    // ---- W slab [32][BN]
+    for (int idx = tid; idx < KS * BN / 4; idx += 256) {
+      const int kk = idx / (BN / 4), c4 = idx - kk * (BN / 4);
+      *reinterpret_cast<float4*>(&Ws[kk * BN + c4 * 4]) =
+          *reinterpret_cast<const float4*>(p.Wt + (size_t)(k0 + kk) * p.ldw + n0 + c4 * 4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KS; kk += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty * 8 + i) * AS_LD + kk]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float bv[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bv[j] = Ws[(kk + k) * BN + tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = k == 0 ? a[i].x : (k == 1 ? a[i].y : (k == 2 ? a[i].z : a[i].w));
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + ty * 8 + i;
+    if (row >= p.M) continue;
+    int f = 0, tau = 0;
+    if (EPI == EPI_PATCH) {
+      const int rr = row / p.tokens, tok = row - rr * p.tokens;
+      f = tok / p.t_n; tau = tok - f * p.t_n;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int col = n0 + tx + 16 * j;
+      float v = acc[i][j] + p.bias[col];
+      if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      if (EPI == EPI_PATCH) { v += p.time_pos[tau * 128 + col]; v += p.freq_pos[f * 128 + col]; }
+      float* dst = p.C + (size_t)row * p.ldc + col;
+      if (EPI == EPI_BIAS_RESID) v = *dst + v;
+      *dst = v;
+    }
+  }
+}
+
+// One warp per (clip-crop, head); lane i < tokens owns query row i.  qkv rows are [q(2x16) | k(2x16) | v(2x16)].
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ o,
+                                                        int RR, int tokens, float scale) {
+  __shared__ float s[4][UITK_MAX_TOKENS * 96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rr0 = blockIdx.x * 4;
+  for (int lr = 0; lr < 4; ++lr) {
+    const int rr = rr0 + lr;
+    if (rr >= RR) break;
+    const float* src = qkv + (size_t)rr * tokens * 96;
+    for (int i = tid; i < tokens * 96; i += 256) s[lr][i] = src[i];
+  }
+  __syncthreads();
+  const int lr = warp >> 1, head = warp & 1;
+  const int rr = rr0 + lr;
+  if (rr >= RR || lane >= tokens) return;
+  const float* base = s[lr];
+  float q[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) q[d] = base[lane * 96 + head * 16 + d];
+  float sc[UITK_MAX_TOKENS];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+    float a = 0.f;
+    if (j < tokens) {
+      const float* kj = base + j * 96 + 32 + head * 16;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) a = fmaf(q[d], kj[d], a);
+      a *= scale;
+      mx = fmaxf(mx, a);
+    }
+    sc[j] = a;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+    sc[j] = j < tokens ? expf(sc[j] - mx) : 0.f;
+    sum += sc[j];
+  }
+  const float inv = 1.f / sum;
+  float out[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) out[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+    if (j < tokens) {
+      const float pj = sc[j] * inv;
+      const float* vj = base + j * 96 + 64 + head * 16;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) out[d] = fmaf(pj, vj[d], out[d]);
+    }
+  }
+  float* dst = o + ((size_t)rr * tokens + lane) * 32 + head * 16;
+#pragma unroll
+  for (int d = 0; d < 16; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(out[d], out[d + 1], out[d + 2], out[d + 3]);
+}
+
+// One CTA per clip: final LN per token, token mean, head LN, Linear + sigmoid, reduce over crops.
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int crops, int tokens,
+                                                   const float* __restrict__ norm_w, const float* __restrict__ norm_b,
+                                                   const float* __restrict__ hln_w, const float* __restrict__ hln_b,
+                                                   const float* __restrict__ head_wt, const float* __restrict__ head_b,
+                                                   int outputdim, int ld_head, int eval_max, float* __restrict__ probs) {
+  __shared__ float part[8][128];
+  __shared__ float pooled[128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t b = blockIdx.x;
+  float accp[3] = {0.f, 0.f, 0.f};
+  if (eval_max) accp[0] = accp[1] = accp[2] = -INFINITY;
+  for (int c = 0; c < crops; ++c) {
+    const float* xc = x + (b * crops + c) * (size_t)tokens * 128;
+    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g = *reinterpret_cast<const float4*>(norm_w + lane * 4);
+    const float4 be = *reinterpret_cast<const float4*>(norm_b + lane * 4);
+    for (int t = warp; t < tokens; t += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(xc + (size_t)t * 128 + lane * 4);
+      float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / 128.f);
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-6f);
+      ps.x += d0 * rstd * g.x + be.x; ps.y += d1 * rstd * g.y + be.y;
+      ps.z += d2 * rstd * g.z + be.z; ps.w += d3 * rstd * g.w + be.w;
+    }
+    __syncthreads();   // previous crop's readers of pooled/part are done
+    *reinterpret_cast<float4*>(&part[warp][lane * 4]) = ps;
+    __syncthreads();
+    if (warp == 0) {
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&part[w][lane * 4]);
+        m.x += t4.x; m.y += t4.y; m.z += t4.z; m.w += t4.w;
+      }
+      const float invn = 1.f / (float)tokens;
+      m.x *= invn; m.y *= invn; m.z *= invn; m.w *= invn;
+      float s = m.x + m.y + m.z + m.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / 128.f);
+      const float d0 = m.x - mean, d1 = m.y - mean, d2 = m.z - mean, d3 = m.w - mean;
+      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
+      const float4 hg = *reinterpret_cast<const float4*>(hln_w + lane * 4);
+      const float4 hb = *reinterpret_cast<const float4*>(hln_b + lane * 4);
+      *reinterpret_cast<float4*>(&pooled[lane * 4]) =
+          make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int oidx = tid + 256 * r;
+      if (oidx < outputdim) {
+        float z = head_b[oidx];
+#pragma unroll 8
+        for (int k = 0; k < 128; ++k) z = fmaf(pooled[k], __ldg(head_wt + (size_t)k * ld_head + oidx), z);
+        const float pr = 1.f / (1.f + expf(-z));
+        accp[r] = eval_max ? fmaxf(accp[r], pr) : accp[r] + pr;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int oidx = tid + 256 * r;
+    if (oidx < outputdim) probs[b * outputdim + oidx] = eval_max ? accp[r] : accp[r] / (float)crops;
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+size_t encoder_fp32_workspace_bytes(int64_t rows) {
+  const size_t r = (size_t)rows;
+  return align_up(r * 128 * 4, 256) + align_up(r * 96 * 4, 256) + align_up(r * 32 * 4, 256) + align_up(r * 384 * 4, 256);
+}
+
+int run_encoder_fp32(const EncoderArgs& a) {
+  const uitk_encoder_cfg& cfg = *a.cfg;
+  const int crops = crops_for(a.T, a.target_length);
+  const int t_n = time_patches_for(a.T, a.target_length);
+  const int tokens = 4 * t_n;
+  const int64_t RR = a.B * crops;
+  const int64_t M64 = RR * tokens;
+  UITK_REQUIRE(M64 < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call (%lld); chunk the batch", (long long)M64);
+  UITK_REQUIRE(cfg.outputdim <= 768, UITK_EINVAL, "outputdim %d > 768 unsupported by the head kernel", cfg.outputdim);
+  UITK_REQUIRE(t_n <= cfg.grid_t, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
+  const int M = (int)M64;
+
+  const EncoderLayout lay = make_encoder_layout(cfg.depth, cfg.outputdim, cfg.grid_t);
+  // the fp32 section starts right after the header (pack.cu)
+  const float* W = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(a.blob) + sizeof(BlobHeader));
+
+  unsigned char* ws = reinterpret_cast<unsigned char*>(a.ws);
+  float* x = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 128 * 4, 256);
+  float* qkv = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 96 * 4, 256);
+  float* o = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 32 * 4, 256);
+  float* h = reinterpret_cast<float*>(ws);
+  UITK_REQUIRE(encoder_fp32_workspace_bytes(M) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
+               encoder_fp32_workspace_bytes(M), a.ws_bytes);
+
+  cudaStream_t s = a.stream;
+  const int mb = (M + BM - 1) / BM;
+  GemmParams p{};
+  p.M = M;
+  // ---- patch embed
+  p.K = 256; p.Wt = W + lay.patch_wt; p.ldw = 128; p.bias = W + lay.patch_b; p.C = x; p.ldc = 128;
+  p.db = a.db; p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
+  p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift; p.max_pow = a.max_pow;
+  p.time_pos = W + lay.time_pos; p.freq_pos = W + lay.freq_pos;
+  gemm_kernel<128, PRO_PATCH, EPI_PATCH><<<dim3(mb, 1), 256, 0, s>>>(p);
+
+  for (int i = 0; i < cfg.depth; ++i) {
+    const float* Wb = W + lay.blocks + (size_t)i * lay.block_stride;
+    GemmParams g{};
+    g.M = M;
+    // LN1 + qkv
+    g.A = x; g.lda = 128; g.K = 128; g.Wt = Wb + lay.blk.qkv_wt; g.ldw = 96; g.bias = Wb + lay.blk.qkv_b;
+    g.C = qkv; g.ldc = 96; g.ln_w = Wb + lay.blk.ln1_w; g.ln_b = Wb + lay.blk.ln1_b; g.ln_eps = 1e-6f;
+    gemm_kernel<96, PRO_LN, EPI_BIAS><<<dim3(mb, 1), 256, 0, s>>>(g);
+    attention_kernel<<<(unsigned)((RR + 3) / 4), 256, 0, s>>>(qkv, o, (int)RR, tokens, 0.125f);
+    // proj + residual
+    g.A = o; g.lda = 32; g.K = 32; g.Wt = Wb + lay.blk.proj_wt; g.ldw = 128; g.bias = Wb + lay.blk.proj_b;
+    g.C = x; g.ldc = 128;
+    gemm_kernel<128, PRO_PLAIN, EPI_BIAS_RESID><<<dim3(mb, 1), 256, 0, s>>>(g);
+    // LN2 + fc1 + ReLU
+    g.A = x; g.lda = 128; g.K = 128; g.Wt = Wb + lay.blk.fc1_wt; g.ldw = 384; g.bias = Wb + lay.blk.fc1_b;
+    g.C = h; g.ldc = 384; g.ln_w = Wb + lay.blk.ln2_w; g.ln_b = Wb + lay.blk.ln2_b;
+    gemm_kernel<128, PRO_LN, EPI_BIAS_RELU><<<dim3(mb, 3), 256, 0, s>>>(g);
+    // fc2 + residual
+    g.A = h; g.lda = 384; g.K = 384; g.Wt = Wb + lay.blk.fc2_wt; g.ldw = 128; g.bias = Wb + lay.blk.fc2_b;
+    g.C = x; g.ldc = 128;
+    gemm_kernel<128, PRO_PLAIN, EPI_BIAS_RESID><<<dim3(mb, 1), 256, 0, s>>>(g);
+  }
+  head_kernel<<<(unsigned)a.B, 256, 0, s>>>(x, crops, tokens, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
+                                            W + lay.head_wt, W + lay.head_b, cfg.outputdim, lay.outputdim_padded,
+                                            a.eval_avg, a.probs);
+  count_launches(2 + 5 * cfg.depth);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+}  // namespace uitk

@@ -1,0 +1,238 @@
+// K1: fused log-mel front-end for sm_100a.
+//
+// Replaces  MelSpectrogram(n_fft 512, win 512, hop 160, center/reflect, power 2, 64 HTK mels) -> 10*log10(max(.,1e-10))
+// (models/uit.py:298-308, 455; torchaudio functional.spectrogram :123-144, MelScale :407-419, amplitude_to_DB :390).
+// The batch-global top-dB clamp (Q2) is NOT applied here: the kernel only tracks the global maximum.
+//
+// One CTA = one chunk of up to 112 frames of one clip, processed as 7 rounds of 16 frames.  A frame's 512-point
+// real DFT is computed as a 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) by 16 threads (half a warp), each
+// holding 16 complex points in registers: radix-16 pass over registers, W256 twiddle, 16x16 transpose through
+// shared memory (warp-synchronous, padded rows), second radix-16 pass, real-FFT unpack, |X|^2, sparse mel
+// (<=2 non-zero filters per bin -> packed ranges), dB.  HBM sees every sample once (frames overlap 3.2x; the
+// overlap is absorbed by the staging buffer / L1) and every output once: 4*L + 4*64*T algorithmic bytes/clip.
+#include "uitk_common.cuh"
+
+namespace uitk {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kFramesPerRound = 16;
+constexpr int kRounds = 7;
+constexpr int kChunk = kFramesPerRound * kRounds;                              // 112 frames / CTA
+constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT;  // 2912
+constexpr int kExStride = 272;                                                 // float2 per frame group (16 x 17)
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// forward radix-4 butterfly (e^{-2 pi i nk/4})
+__device__ __forceinline__ void fft4(float2& a, float2& b, float2& c, float2& d) {
+  float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d);
+  float2 t3 = make_float2(b.y - d.y, d.x - b.x);   // (b - d) * (-i)
+  a = cadd(t0, t2); b = cadd(t1, t3); c = csub(t0, t2); d = csub(t1, t3);
+}
+
+// in-register forward 16-point DFT, natural order in and out
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) fft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+  // twiddles W16^(n1*k1): v[n1 + 4*k1]
+  v[1 + 4] = cmul(v[1 + 4], make_float2(c1, -s1));    // W^1
+  v[1 + 8] = cmul(v[1 + 8], make_float2(h, -h));      // W^2
+  v[1 + 12] = cmul(v[1 + 12], make_float2(s1, -c1));  // W^3
+  v[2 + 4] = cmul(v[2 + 4], make_float2(h, -h));      // W^2
+  v[2 + 8] = make_float2(v[2 + 8].y, -v[2 + 8].x);    // W^4 = -i
+  v[2 + 12] = cmul(v[2 + 12], make_float2(-h, -h));   // W^6
+  v[3 + 4] = cmul(v[3 + 4], make_float2(s1, -c1));    // W^3
+  v[3 + 8] = cmul(v[3 + 8], make_float2(-h, -h));     // W^6
+  v[3 + 12] = cmul(v[3 + 12], make_float2(-c1, s1));  // W^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // V[k1 + 4*k2] sits in v[4*k1 + k2]: 4x4 register transpose
+  float2 t;
+  t = v[1]; v[1] = v[4]; v[4] = t;
+  t = v[2]; v[2] = v[8]; v[8] = t;
+  t = v[3]; v[3] = v[12]; v[12] = t;
+  t = v[6]; v[6] = v[9]; v[9] = t;
+  t = v[7]; v[7] = v[13]; v[13] = t;
+  t = v[11]; v[11] = v[14]; v[14] = t;
+}
+
+struct SmemLayout {
+  float window[512];
+  float2 tw256[256];
+  float2 tw512[256];
+  int mel_lo[64], mel_cnt[64], mel_off[64];
+  float x[kSamplesPerRound];
+  float2 ex[kFramesPerRound * kExStride];
+  float out[64 * 17];
+  float red[8];
+  // followed by mel_w[n_weights]
+};
+
+__global__ void __launch_bounds__(kThreads, 3)
+logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
+              const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
+  float* s_melw = reinterpret_cast<float*>(smem_raw + sizeof(SmemLayout));
+
+  const int tid = threadIdx.x;
+  const int g = tid >> 4;      // frame slot in the round
+  const int j = tid & 15;      // lane within the frame group
+  const long long b = blockIdx.y;
+  const int t_chunk0 = blockIdx.x * kChunk;
+
+  for (int i = tid; i < 512; i += kThreads) S.window[i] = blob->window[i];
+  S.tw256[tid] = blob->tw256[tid];
+  S.tw512[tid] = blob->tw512[tid];
+  if (tid < 64) {
+    S.mel_lo[tid] = blob->mel_lo[tid];
+    S.mel_cnt[tid] = blob->mel_cnt[tid];
+    S.mel_off[tid] = blob->mel_off[tid];
+  }
+  const int nw = blob->n_weights;
+  for (int i = tid; i < nw; i += kThreads) s_melw[i] = blob->mel_w[i];
+
+  const float* clip = wav + b * ld;
+  float* out_clip = db + b * 64 * (long long)T;
+  float tmax = 0.f;
+
+  for (int round = 0; round < kRounds; ++round) {
+    const int t0 = t_chunk0 + round * kFramesPerRound;
+    if (t0 >= T) break;
+    __syncthreads();   // constants visible; previous round finished with S.x / S.out
+    {
+      const long long s0 = (long long)t0 * UITK_HOP - UITK_N_FFT / 2;
+      for (int i = tid; i < kSamplesPerRound; i += kThreads) {
+        long long idx = s0 + i;
+        if (idx < 0) idx = -idx;                       // reflect (no edge repeat)
+        if (idx >= L) idx = 2 * (L - 1) - idx;
+        S.x[i] = (idx >= 0 && idx < L) ? __ldg(clip + idx) : 0.f;   // frames past T read zeros
+      }
+    }
+    __syncthreads();
+
+    // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
+    float2 v[16];
+    const float* xf = S.x + g * UITK_HOP;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int n = j + 16 * m;
+      const float2 xx = *reinterpret_cast<const float2*>(xf + 2 * n);
+      const float2 ww = *reinterpret_cast<const float2*>(S.window + 2 * n);
+      v[m] = make_float2(xx.x * ww.x, xx.y * ww.y);
+    }
+    fft16(v);                                   // over m -> k1
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], S.tw256[j * k1]);
+    float2* e = S.ex + g * kExStride;
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + j] = v[k1];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = e[j * 17 + n1];   // this thread now owns k1 = j
+    __syncwarp();
+    fft16(v);                                   // over n1 -> k2 ; v[k2] = Z[j + 16 k2]
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) e[j + 16 * k2] = v[k2];
+    __syncwarp();
+
+    // ---- real-FFT unpack + power: X[k] = E[k] + W512^k O[k]
+    float p[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int k = j + 16 * m;
+      const float2 zk = v[m];
+      const float2 zn = e[(256 - k) & 255];
+      const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
+      const float orr = 0.5f * (zk.y + zn.y), oi = -0.5f * (zk.x - zn.x);
+      const float2 w = S.tw512[k];
+      const float xr = er + (orr * w.x - oi * w.y);
+      const float xi = ei + (orr * w.y + oi * w.x);
+      p[m] = xr * xr + xi * xi;
+    }
+    __syncwarp();
+    float* pf = reinterpret_cast<float*>(e);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) pf[j + 16 * m] = p[m];
+    if (j == 0) {
+      const float ny = v[0].x - v[0].y;         // X[256] = Re Z0 - Im Z0
+      pf[256] = ny * ny;
+    }
+    __syncwarp();
+
+    // ---- sparse mel + dB
+    const bool live = (t0 + g) < T;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = j + 16 * q;
+      const int lo = S.mel_lo[m], cnt = S.mel_cnt[m], off = S.mel_off[m];
+      float acc = 0.f;
+      for (int i = 0; i < cnt; ++i) acc = fmaf(s_melw[off + i], pf[lo + i], acc);
+      if (live) tmax = fmaxf(tmax, acc);
+      S.out[m * 17 + g] = 10.f * log10f(fmaxf(acc, 1e-10f));
+    }
+    __syncthreads();
+    for (int i = tid; i < 64 * kFramesPerRound; i += kThreads) {
+      const int m = i >> 4, gg = i & 15;
+      const int t = t0 + gg;
+      if (t < T) out_clip[(long long)m * T + t] = S.out[m * 17 + gg];
+    }
+  }
+
+  // ---- global max of the mel power (non-negative: uint order == float order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  __syncthreads();
+  if ((tid & 31) == 0) S.red[tid >> 5] = tmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = S.red[0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, S.red[w]);
+    atomicMax(max_pow, __float_as_uint(m));
+  }
+}
+
+__global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint32_t* __restrict__ max_pow, float top_db) {
+  const float cutoff = 10.f * log10f(fmaxf(__uint_as_float(*max_pow), 1e-10f)) - top_db;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) db[i] = fmaxf(db[i], cutoff);
+}
+
+}  // namespace
+
+int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
+                  uint32_t* max_pow, cudaStream_t s) {
+  const int64_t T = 1 + L / UITK_HOP;
+  const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
+  UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int chunks = (int)((T + kChunk - 1) / kChunk);
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = (int)((B - b0) < 65535 ? (B - b0) : 65535);
+    dim3 grid(chunks, nb);
+    logmel_kernel<<<grid, kThreads, smem, s>>>(wav + b0 * ld, (long long)L, (long long)ld, (int)T, blob,
+                                               db + b0 * 64 * T, max_pow);
+    count_launches(1);
+  }
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, float top_db, cudaStream_t s) {
+  if (n == 0) return UITK_OK;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  clamp_db_kernel<<<blocks, 256, 0, s>>>(db, (long long)n, max_pow, top_db);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+}  // namespace uitk

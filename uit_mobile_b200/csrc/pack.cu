@@ -1,0 +1,191 @@
+// Host-side packing of state_dict tensors into the kernels' device layouts (no CUDA calls here).
+#include <math.h>
+#include <stdarg.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "uitk_common.cuh"
+
+namespace uitk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long get_launches() { return g_launches.load(std::memory_order_relaxed); }
+
+static size_t take(size_t& cur, size_t n) {
+  const size_t off = cur;
+  cur += (n + 63) / 64 * 64;   // 256-byte alignment of every tensor
+  return off;
+}
+
+EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
+  EncoderLayout l{};
+  l.depth = depth; l.outputdim = outputdim; l.grid_t = grid_t;
+  l.outputdim_padded = (outputdim + 3) / 4 * 4;
+  size_t cur = 0;
+  l.bn_scale = take(cur, 64); l.bn_shift = take(cur, 64);
+  l.patch_wt = take(cur, 256 * 128); l.patch_b = take(cur, 128);
+  l.time_pos = take(cur, (size_t)grid_t * 128); l.freq_pos = take(cur, 4 * 128);
+  l.norm_w = take(cur, 128); l.norm_b = take(cur, 128);
+  l.hln_w = take(cur, 128); l.hln_b = take(cur, 128);
+  l.head_wt = take(cur, (size_t)128 * l.outputdim_padded); l.head_b = take(cur, l.outputdim_padded);
+  l.blocks = cur;
+  size_t b = 0;
+  l.blk.ln1_w = take(b, 128); l.blk.ln1_b = take(b, 128);
+  l.blk.qkv_wt = take(b, 128 * 96); l.blk.qkv_b = take(b, 96);
+  l.blk.proj_wt = take(b, 32 * 128); l.blk.proj_b = take(b, 128);
+  l.blk.ln2_w = take(b, 128); l.blk.ln2_b = take(b, 128);
+  l.blk.fc1_wt = take(b, 128 * 384); l.blk.fc1_b = take(b, 384);
+  l.blk.fc2_wt = take(b, 384 * 128); l.blk.fc2_b = take(b, 128);
+  l.block_stride = b;
+  l.total_floats = cur + b * (size_t)depth;
+  return l;
+}
+
+// Order of h_tensors[] (state_dict keys).  Dead keys for pooling='mean' (cls_token,
+// token_pos_embed; Q4), the front-end buffers and num_batches_tracked are not passed.
+static const char* kFixedNames[] = {
+    "init_bn.1.weight", "init_bn.1.bias", "init_bn.1.running_mean", "init_bn.1.running_var",
+    "patch_embed.proj.weight", "patch_embed.proj.bias", "time_pos_embed", "freq_pos_embed",
+    "norm.weight", "norm.bias", "outputlayer.0.weight", "outputlayer.0.bias",
+    "outputlayer.1.weight", "outputlayer.1.bias"};
+static const char* kBlockNames[] = {
+    "norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+    "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"};
+constexpr int kNumFixed = 14, kNumBlock = 12;
+
+static void transpose_into(float* dst, const float* w, int out_f, int in_f, int ld_dst) {
+  // torch Linear weight [out_f][in_f] -> Wt[in_f][ld_dst]
+  for (int o = 0; o < out_f; ++o)
+    for (int k = 0; k < in_f; ++k) dst[(size_t)k * ld_dst + o] = w[(size_t)o * in_f + k];
+}
+
+}  // namespace uitk
+
+using namespace uitk;
+
+extern "C" {
+
+int uitk_version(void) { return UITK_VERSION; }
+const char* uitk_last_error(void) { return get_error(); }
+uint64_t uitk_kernel_launches(void) { return get_launches(); }
+
+int64_t uitk_num_frames(int64_t L) { return 1 + L / UITK_HOP; }
+int uitk_num_crops(int64_t T, int target_length) { return crops_for(T, target_length); }
+int uitk_tokens_per_crop(int64_t T, int target_length) { return 4 * time_patches_for(T, target_length); }
+
+size_t uitk_frontend_blob_bytes(const float* h_fb) { (void)h_fb; return sizeof(FrontendBlob); }
+
+int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, size_t blob_bytes) {
+  UITK_REQUIRE(h_window && h_fb && h_blob, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(blob_bytes >= sizeof(FrontendBlob), UITK_ENOSPACE, "front-end blob needs %zu bytes", sizeof(FrontendBlob));
+  FrontendBlob* fb = reinterpret_cast<FrontendBlob*>(h_blob);
+  memset(fb, 0, sizeof(FrontendBlob));
+  fb->magic = kFrontendMagic;
+  memcpy(fb->window, h_window, sizeof(float) * 512);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int j = 0; j < 256; ++j) {
+    fb->tw256[j] = make_float2((float)cos(two_pi * j / 256.0), (float)-sin(two_pi * j / 256.0));
+    fb->tw512[j] = make_float2((float)cos(two_pi * j / 512.0), (float)-sin(two_pi * j / 512.0));
+  }
+  int n = 0;
+  for (int m = 0; m < UITK_N_MELS; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < UITK_N_FREQS; ++k)
+      if (h_fb[(size_t)k * UITK_N_MELS + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    if (lo < 0) { fb->mel_lo[m] = 0; fb->mel_cnt[m] = 0; fb->mel_off[m] = n; continue; }
+    const int cnt = hi - lo + 1;
+    UITK_REQUIRE(n + cnt <= kMaxMelWeights, UITK_EINVAL,
+                 "mel filterbank too dense for the kernel (%d packed weights max)", kMaxMelWeights);
+    fb->mel_lo[m] = lo; fb->mel_cnt[m] = cnt; fb->mel_off[m] = n;
+    for (int k = lo; k <= hi; ++k) fb->mel_w[n++] = h_fb[(size_t)k * UITK_N_MELS + m];
+  }
+  fb->n_weights = n;
+  return UITK_OK;
+}
+
+int uitk_encoder_num_tensors(int depth) { return kNumFixed + kNumBlock * depth; }
+
+const char* uitk_encoder_tensor_name(int depth, int index) {
+  static thread_local std::string name;
+  if (index < 0 || index >= uitk_encoder_num_tensors(depth)) return nullptr;
+  if (index < kNumFixed) return kFixedNames[index];
+  const int i = (index - kNumFixed) / kNumBlock, j = (index - kNumFixed) % kNumBlock;
+  name = "blocks." + std::to_string(i) + "." + kBlockNames[j];
+  return name.c_str();
+}
+
+static int check_cfg(const uitk_encoder_cfg* cfg) {
+  UITK_REQUIRE(cfg, UITK_EINVAL, "null cfg");
+  UITK_REQUIRE(cfg->depth >= 1 && cfg->depth <= 64, UITK_EINVAL, "depth %d out of range", cfg->depth);
+  UITK_REQUIRE(cfg->outputdim >= 1 && cfg->outputdim <= 768, UITK_EINVAL, "outputdim %d out of range [1,768]", cfg->outputdim);
+  UITK_REQUIRE(cfg->grid_t >= 1 && cfg->grid_t <= 6, UITK_EINVAL, "grid_t %d out of range [1,6]", cfg->grid_t);
+  UITK_REQUIRE(cfg->precision == UITK_PREC_FP32 || cfg->precision == UITK_PREC_BF16, UITK_EINVAL, "bad precision %d", cfg->precision);
+  return UITK_OK;
+}
+
+size_t uitk_encoder_blob_bytes(const uitk_encoder_cfg* cfg) {
+  if (check_cfg(cfg) != UITK_OK) return 0;
+  const EncoderLayout l = make_encoder_layout(cfg->depth, cfg->outputdim, cfg->grid_t);
+  return sizeof(BlobHeader) + l.total_floats * sizeof(float);
+}
+
+int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* h_blob, size_t blob_bytes) {
+  int rc = check_cfg(cfg);
+  if (rc != UITK_OK) return rc;
+  UITK_REQUIRE(t && h_blob, UITK_EINVAL, "null pointer");
+  const size_t need = uitk_encoder_blob_bytes(cfg);
+  UITK_REQUIRE(blob_bytes >= need, UITK_ENOSPACE, "encoder blob needs %zu bytes, have %zu", need, blob_bytes);
+  for (int i = 0; i < uitk_encoder_num_tensors(cfg->depth); ++i)
+    UITK_REQUIRE(t[i], UITK_EINVAL, "tensor %d (%s) is null", i, uitk_encoder_tensor_name(cfg->depth, i));
+  const EncoderLayout l = make_encoder_layout(cfg->depth, cfg->outputdim, cfg->grid_t);
+  memset(h_blob, 0, need);
+  BlobHeader* hdr = reinterpret_cast<BlobHeader*>(h_blob);
+  hdr->magic = kEncoderMagic; hdr->depth = cfg->depth; hdr->outputdim = cfg->outputdim; hdr->grid_t = cfg->grid_t;
+  hdr->precision = cfg->precision; hdr->fp32_offset = sizeof(BlobHeader); hdr->bf16_offset = 0; hdr->total_bytes = need;
+  float* W = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h_blob) + sizeof(BlobHeader));
+
+  // eval BatchNorm folded the way ATen does it: alpha = w / sqrt(var + eps); beta = b - mean * alpha
+  const float *bn_w = t[0], *bn_b = t[1], *bn_m = t[2], *bn_v = t[3];
+  for (int m = 0; m < 64; ++m) {
+    const float invstd = 1.f / sqrtf(bn_v[m] + 1e-5f);
+    const float alpha = invstd * bn_w[m];
+    W[l.bn_scale + m] = alpha;
+    W[l.bn_shift + m] = bn_b[m] - bn_m[m] * alpha;
+  }
+  transpose_into(W + l.patch_wt, t[4], 128, 256, 128);                 // [128,1,16,16] -> [256][128], k = df*16+dt
+  memcpy(W + l.patch_b, t[5], 128 * sizeof(float));
+  for (int c = 0; c < 128; ++c) {
+    for (int tt = 0; tt < cfg->grid_t; ++tt) W[l.time_pos + (size_t)tt * 128 + c] = t[6][(size_t)c * cfg->grid_t + tt];
+    for (int f = 0; f < 4; ++f) W[l.freq_pos + (size_t)f * 128 + c] = t[7][(size_t)c * 4 + f];
+  }
+  memcpy(W + l.norm_w, t[8], 128 * sizeof(float)); memcpy(W + l.norm_b, t[9], 128 * sizeof(float));
+  memcpy(W + l.hln_w, t[10], 128 * sizeof(float)); memcpy(W + l.hln_b, t[11], 128 * sizeof(float));
+  transpose_into(W + l.head_wt, t[12], cfg->outputdim, 128, l.outputdim_padded);
+  memcpy(W + l.head_b, t[13], cfg->outputdim * sizeof(float));
+  for (int i = 0; i < cfg->depth; ++i) {
+    const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
+    float* Wb = W + l.blocks + (size_t)i * l.block_stride;
+    memcpy(Wb + l.blk.ln1_w, b[0], 128 * 4); memcpy(Wb + l.blk.ln1_b, b[1], 128 * 4);
+    transpose_into(Wb + l.blk.qkv_wt, b[2], 96, 128, 96); memcpy(Wb + l.blk.qkv_b, b[3], 96 * 4);
+    transpose_into(Wb + l.blk.proj_wt, b[4], 128, 32, 128); memcpy(Wb + l.blk.proj_b, b[5], 128 * 4);
+    memcpy(Wb + l.blk.ln2_w, b[6], 128 * 4); memcpy(Wb + l.blk.ln2_b, b[7], 128 * 4);
+    transpose_into(Wb + l.blk.fc1_wt, b[8], 384, 128, 384); memcpy(Wb + l.blk.fc1_b, b[9], 384 * 4);
+    transpose_into(Wb + l.blk.fc2_wt, b[10], 128, 384, 128); memcpy(Wb + l.blk.fc2_b, b[11], 128 * 4);
+  }
+  return UITK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+"""Drop-in mirror of the reference's ``models/uit.py`` for the batched-inference hot path on B200.
+
+Same factory names (``uit_xs / uit_xxs / uit_xxxs``), same constructor kwargs, same ``state_dict`` keys / shapes /
+dtypes, same ``forward(x[B, L]) -> [B, outputdim]`` sigmoid scores (reference: models/uit.py:252-493, 581-655).
+The arithmetic is NOT here: ``forward`` calls the hand-written sm_100a kernels in ``libuitk.so`` through the C ABI
+declared in ``include/uitk.h``.  The sub-modules below are parameter holders that keep the reference's
+state_dict layout; calling them directly raises.  There is no CPU path and no PyTorch fallback: a model that is
+not on a CUDA device, is in training mode, or is configured outside what the kernels implement raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+
+__all__ = ["UITBase", "uit_xs", "uit_xxs", "uit_xxxs", "PRETRAINED_CHECKPOINTS"]
+
+
+class _Holder(nn.Module):
+    """Parameter container: arithmetic lives in the fused CUDA kernels."""
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError(f"{type(self).__name__} only holds parameters; run the whole model (UITBase.forward), "
+                           "the hot path is fused CUDA with no per-layer PyTorch fallback")
+
+
+class _Linear(_Holder):
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+        nn.init.trunc_normal_(self.weight, std=.02)          # uit.py:369-373
+
+
+class _LayerNorm(_Holder):
+    def __init__(self, dim: int, eps: float):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class _BatchNorm(_Holder):
+    """Eval-mode BatchNorm2d(64, momentum=0.01) state (uit.py:310-313)."""
+
+    def __init__(self, n: int):
+        super().__init__()
+        self.eps, self.momentum = 1e-5, 0.01
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _Conv(_Holder):
+    def __init__(self, out_ch: int, k: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_ch, 1, k, k))
+        self.bias = nn.Parameter(torch.empty(out_ch))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))   # nn.Conv2d.reset_parameters
+        bound = 1.0 / math.sqrt(k * k)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class AudioPatchEmbed(_Holder):
+    """uit.py:43-74 (flatten=False, norm=Identity)."""
+
+    def __init__(self, input_size, patch_size: int, patch_stride: int, embed_dim: int):
+        super().__init__()
+        self.input_size = tuple(input_size)
+        self.patch_size = (patch_size, patch_size)
+        self.grid_size = (input_size[0] // patch_stride, input_size[1] // patch_stride)
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.flatten = False
+        self.proj = _Conv(embed_dim, patch_size)
+        self.norm = nn.Identity()
+
+
+class BNeckAttention(_Holder):
+    """uit.py:89-122."""
+
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5          # 0.125: from the UN-bottlenecked head dim (Q3)
+        self.inner_dim = dim // 4
+        self.qkv = _Linear(dim, self.inner_dim * 3)
+        self.proj = _Linear(self.inner_dim, dim)
+
+
+class Mlp(_Holder):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = _Linear(dim, hidden)
+        self.fc2 = _Linear(hidden, dim)
+
+
+class Block(_Holder):
+    """uit.py:206-248 with LayerScale / DropPath = Identity."""
+
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float):
+        super().__init__()
+        self.norm1 = _LayerNorm(dim, 1e-6)
+        self.attn = BNeckAttention(dim, num_heads)
+        self.norm2 = _LayerNorm(dim, 1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+
+class _Spectrogram(_Holder):
+    def __init__(self, n_fft: int):
+        super().__init__()
+        self.register_buffer("window", torch.hann_window(n_fft, periodic=True))
+
+
+def _melscale_fbanks_htk(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """HTK triangular filterbank, torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk')."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+class _MelScale(_Holder):
+    def __init__(self, f_min, f_max, n_mels, n_fft):
+        super().__init__()
+        self.register_buffer("fb", _melscale_fbanks_htk(n_fft // 2 + 1, float(f_min), float(f_max), n_mels, 16000))
+
+
+class MelSpectrogram(_Holder):
+    """Holds ``spectrogram.window`` / ``mel_scale.fb`` (persistent buffers of the reference's front-end, Q9)."""
+
+    def __init__(self, f_min, f_max, n_mels, n_fft):
+        super().__init__()
+        self.spectrogram = _Spectrogram(n_fft)
+        self.mel_scale = _MelScale(f_min, f_max, n_mels, n_fft)
+
+
+class AmplitudeToDB(_Holder):
+    def __init__(self, top_db: float):
+        super().__init__()
+        self.top_db = top_db
+
+
+class FrontEnd(nn.Sequential):
+    """``front_end`` of the reference (uit.py:298-308): log-mel in dB with the batch-global top-dB clamp,
+    [B, L] -> [B, 64, T], computed by the fused CUDA kernel."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        db, max_pow = self.logmel_unclamped(x)
+        n = db.numel()
+        N.check(N.lib().uitk_clamp_db(db.data_ptr(), n, max_pow.data_ptr(), float(self[1].top_db),
+                                      torch.cuda.current_stream(db.device).cuda_stream), "uitk_clamp_db")
+        return db
+
+    def _blob(self, device: torch.device) -> torch.Tensor:
+        win, fb = self[0].spectrogram.window, self[0].mel_scale.fb
+        key = (str(device), win._version, fb._version, win.data_ptr(), fb.data_ptr())
+        cache = self.__dict__.setdefault("_uitk_cache", {})
+        if cache.get("key") != key:
+            l = N.lib()
+            w = win.detach().to("cpu", torch.float32).contiguous()
+            f = fb.detach().to("cpu", torch.float32).contiguous()
+            if tuple(w.shape) != (512,) or tuple(f.shape) != (257, 64):
+                raise N.UitkError("the log-mel kernel implements n_fft=win=512, hop=160, 64 mels only")
+            host = torch.zeros(l.uitk_frontend_blob_bytes(f.data_ptr()), dtype=torch.uint8)
+            N.check(l.uitk_pack_frontend(w.data_ptr(), f.data_ptr(), host.data_ptr(), host.numel()), "uitk_pack_frontend")
+            cache["key"], cache["blob"] = key, host.to(device)
+        return cache["blob"]
+
+    def logmel_unclamped(self, x: torch.Tensor, ld: Optional[int] = None, B: Optional[int] = None, L: Optional[int] = None,
+                         out: Optional[torch.Tensor] = None, max_pow: Optional[torch.Tensor] = None):
+        """Launch K1.  Returns (dB [B,64,T] un-clamped, max-power word [1] int32).  ``ld/B/L`` describe strided
+        views (sliding windows over one long stream) without materialising them.  ``out`` / ``max_pow`` let a
+        pipelined caller write chunks of one batch into a shared buffer and keep ONE running maximum (Q2)."""
+        if not x.is_cuda:
+            raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
+        if x.dtype != torch.float32:
+            raise N.UitkError(f"expected float32 waveform, got {x.dtype}")
+        if B is None:
+            if x.dim() != 2:
+                raise ValueError(f"expected a [B, L] waveform batch, got shape {tuple(x.shape)}")
+            if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < 1):
+                x = x.contiguous()
+            B, L = x.shape
+            ld = x.stride(0) if B > 1 else L
+        l = N.lib()
+        T = int(l.uitk_num_frames(L))
+        if out is None:
+            out = torch.empty((B, 64, T), dtype=torch.float32, device=x.device)
+        elif tuple(out.shape) != (B, 64, T) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("out must be a contiguous float32 [B, 64, T] tensor")
+        if max_pow is None:
+            max_pow = torch.zeros(1, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(l.uitk_logmel(x.data_ptr(), B, L, ld, self._blob(x.device).data_ptr(), out.data_ptr(),
+                                  max_pow.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "uitk_logmel")
+        return out, max_pow
+
+
+class UITBase(nn.Module):
+    """uit.py:252-493, inference path only (eval mode, pooling='mean', BNeckAttention, ReLU MLP, init_bn)."""
+
+    def __init__(self, outputdim=527, patch_size=16, patch_stride=16, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., init_bn: bool = True,
+                 norm_layer=None, act_layer=None, init_values=None, target_length=1012, pooling='token',
+                 wavtransforms=None, spectransforms=None, time_patch_out: Optional[float] = None,
+                 freq_patch_out: Optional[float] = None, block_type='Block', attention_type='Attention',
+                 eval_avg='mean', precision: str = "fp32", process_group=None, **kwargs):
+        super().__init__()
+        assert pooling in ('mean', 'token', 'dm')
+        self.outputdim, self.pooling, self.embed_dim = outputdim, pooling, embed_dim
+        self.patch_stride, self.patch_size = patch_stride, patch_size
+        self.n_mels = kwargs.get('n_mels', 64)
+        n_fft = kwargs.get('n_fft', 512)
+        self.hop_size = kwargs.get('hop_size', 160)
+        self.win_size = kwargs.get('win_size', 512)
+        f_min, f_max = kwargs.get('f_min', 0), kwargs.get('f_max', 8000)
+        self.center = kwargs.get('center', True)
+        self.eval_avg = eval_avg
+        self.time_patch_out, self.freq_patch_out = time_patch_out, freq_patch_out
+        self.target_length = target_length
+        self.depth, self.num_heads, self.mlp_ratio = depth, num_heads, mlp_ratio
+        self.precision = precision
+        self.process_group = process_group          # batch-sharded inference: all-reduce(max) of the top-dB scope
+        self.max_clips_per_launch = 16384
+
+        # Everything the kernels do not implement is refused up front (no silent fallback).
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"uit_mobile_b200 implements the UiT-XS/XXS/XXXS inference path only: {what}")
+        need(pooling == 'mean', f"pooling={pooling!r} (only 'mean')")
+        need(attention_type == 'BNeckAttention', f"attention_type={attention_type!r} (only 'BNeckAttention')")
+        need(block_type == 'Block', f"block_type={block_type!r}")
+        need(act_layer is nn.ReLU, "act_layer must be nn.ReLU")
+        need(init_bn, "init_bn=False")
+        need(embed_dim == 128 and num_heads == 2 and float(mlp_ratio) == 3.0, "embed_dim/num_heads/mlp_ratio != 128/2/3.0")
+        need(patch_size == 16 and patch_stride == 16, "patch_size/stride != 16")
+        need(self.n_mels == 64 and n_fft == 512 and self.hop_size == 160 and self.win_size == 512 and self.center,
+             "front-end other than n_mels=64, n_fft=win=512, hop=160, center=True")
+        need(init_values is None and drop_rate == 0. and attn_drop_rate == 0. and drop_path_rate == 0., "LayerScale/dropout/drop-path")
+        need(qkv_bias, "qkv_bias=False")
+        need(norm_layer is None, "custom norm_layer")
+        need(16 <= target_length <= 111, f"target_length={target_length} (16..111 frames, i.e. at most 6 time patches)")
+        need(1 <= outputdim <= 768, f"outputdim={outputdim}")
+        need(eval_avg in ('mean', 'max'), f"eval_avg={eval_avg!r}")
+        need(precision in N.PRECISIONS, f"precision={precision!r} (fp32 or bf16)")
+
+        self.front_end = FrontEnd(MelSpectrogram(f_min, f_max, self.n_mels, n_fft), AmplitudeToDB(top_db=120))
+        self.init_bn = nn.Sequential(nn.Identity(), _BatchNorm(self.n_mels), nn.Identity())
+        self.patch_embed = AudioPatchEmbed((self.n_mels, target_length), patch_size, patch_stride, embed_dim)
+        self.spectransforms = nn.Sequential() if spectransforms is None else spectransforms
+        self.wavtransforms = nn.Sequential() if wavtransforms is None else wavtransforms
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.token_pos_embed = nn.Parameter(torch.randn(1, embed_dim) * .02)
+        self.time_pos_embed = nn.Parameter(torch.randn(1, embed_dim, 1, self.patch_embed.grid_size[1]) * .02)
+        self.freq_pos_embed = nn.Parameter(torch.randn(1, embed_dim, self.patch_embed.grid_size[0], 1) * .02)
+        self.pos_drop = nn.Identity()
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        self.norm = _LayerNorm(embed_dim, 1e-6)
+        self.outputlayer = nn.Sequential(_LayerNorm(embed_dim, 1e-5), _Linear(embed_dim, outputdim))
+        nn.init.normal_(self.cls_token, std=1e-6)
+        self._packed: Dict = {}
+
+    # ---- reference API surface -----------------------------------------------------------------------------
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'time_pos_embed', 'cls_token', 'freq_pos_embed', 'token_pos_embed'}
+
+    def load_state_dict(self, state_dict, strict=True):
+        """uit.py:416-450: slice / bilinearly resize the positional embeddings when shapes differ."""
+        if 'time_pos_embed' in state_dict and self.time_pos_embed.shape != state_dict['time_pos_embed'].shape:
+            state_dict = dict(state_dict)
+            self.change_pos_embedding(state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def change_pos_embedding(self, state_dict):
+        tt, tf = self.time_pos_embed.shape[-1], self.freq_pos_embed.shape[-2]
+        pt, pf = state_dict['time_pos_embed'], state_dict['freq_pos_embed']
+        if tt <= pt.shape[-1]:
+            state_dict['time_pos_embed'] = pt[..., :tt]
+        else:
+            state_dict['time_pos_embed'] = torch.nn.functional.interpolate(pt, size=(1, tt), align_corners=False, mode='bilinear')
+        if tf <= pf.shape[-2]:
+            state_dict['freq_pos_embed'] = pf[:, :, :tf, :]
+        else:
+            state_dict['freq_pos_embed'] = torch.nn.functional.interpolate(pf, size=(tf, 1), align_corners=False, mode='bilinear')
+
+    def train(self, mode: bool = True):
+        # The module can be flipped like any nn.Module, but only the eval path is implemented (Q11).
+        return super().train(mode)
+
+    # ---- kernel plumbing -----------------------------------------------------------------------------------------
+    def _cfg(self) -> N.EncoderCfg:
+        return N.EncoderCfg(self.depth, self.outputdim, self.patch_embed.grid_size[1], N.PRECISIONS[self.precision])
+
+    def _encoder_blob(self, device: torch.device) -> torch.Tensor:
+        """Pack the state_dict into the kernel layout (lazily; re-packed when any tensor changed)."""
+        tensors = self.__dict__.get("_packed_tensors")
+        if tensors is None:
+            sd = dict(self.named_parameters())
+            sd.update(dict(self.named_buffers()))
+            tensors = [sd[n] for n in N.encoder_tensor_names(self.depth)]
+            self.__dict__["_packed_tensors"] = tensors
+        key = (str(device), self.precision) + tuple((t._version, t.data_ptr()) for t in tensors)
+        if self._packed.get("key") != key:
+            l = N.lib()
+            cfg = self._cfg()
+            host = [t.detach().to("cpu", torch.float32).contiguous() for t in tensors]
+            ptrs = (C.c_void_p * len(host))(*[h.data_ptr() for h in host])
+            nbytes = l.uitk_encoder_blob_bytes(C.byref(cfg))
+            if nbytes == 0:
+                N.check(-1, "uitk_encoder_blob_bytes")
+            blob = torch.zeros(nbytes, dtype=torch.uint8)
+            N.check(l.uitk_pack_encoder(C.byref(cfg), ptrs, blob.data_ptr(), nbytes), "uitk_pack_encoder")
+            self._packed = {"key": key, "blob": blob.to(device)}
+        return self._packed["blob"]
+
+    def encode(self, db: torch.Tensor, max_pow: torch.Tensor) -> torch.Tensor:
+        """init_bn + crops + forward_features + forward_head on un-clamped log-mel (uit.py:460-492)."""
+        l = N.lib()
+        B, _, T = db.shape
+        cfg = self._cfg()
+        blob = self._encoder_blob(db.device)
+        probs = torch.empty((B, self.outputdim), dtype=torch.float32, device=db.device)
+        step = max(1, self.max_clips_per_launch // int(l.uitk_num_crops(T, self.target_length)))
+        stream = torch.cuda.current_stream(db.device).cuda_stream
+        with torch.cuda.device(db.device):
+            ws = None
+            for b0 in range(0, B, step):
+                nb = min(step, B - b0)
+                need = l.uitk_encoder_workspace_bytes(C.byref(cfg), nb, T, self.target_length)
+                if need == 0:
+                    N.check(-1, "uitk_encoder_workspace_bytes")
+                if ws is None or ws.numel() < need:
+                    ws = torch.empty(need, dtype=torch.uint8, device=db.device)
+                N.check(l.uitk_encoder(C.byref(cfg), blob.data_ptr(), db[b0:b0 + nb].data_ptr(), nb, T, self.target_length,
+                                       1 if self.eval_avg == 'max' else 0, max_pow.data_ptr(), probs[b0:b0 + nb].data_ptr(),
+                                       ws.data_ptr(), ws.numel(), stream), "uitk_encoder")
+            self._last_workspace = ws
+        return probs
+
+    def forward(self, x: torch.Tensor, mixup=None) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("uit_mobile_b200 implements inference only: call model.eval() "
+                                      "(training branches of uit.py:453-459 are out of scope)")
+        if self.eval_avg not in ('mean', 'max'):
+            raise ValueError(f'Unknown Eval average function ({self.eval_avg})')
+        db, max_pow = self.front_end.logmel_unclamped(x)
+        if self.process_group is not None:
+            # Q2: the top-dB cutoff is batch-global; with the batch sharded over GPUs the scope is the global batch.
+            torch.distributed.all_reduce(max_pow, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
+        return self.encode(db, max_pow)
+
+
+def _factory(depth: int, kwargs) -> UITBase:
+    model_kwargs = dict(patch_size=16, embed_dim=128, depth=depth, num_heads=2, mlp_ratio=3.0, pooling='mean',
+                        init_bn=True, drop_path_rate=0.0, act_layer=nn.ReLU, attention_type='BNeckAttention')
+    model_kwargs = {**model_kwargs, **kwargs}
+    return UITBase(**model_kwargs)
+
+
+def uit_xs(**kwargs):       # uit.py:581-597
+    return _factory(12, kwargs)
+
+
+def uit_xxs(**kwargs):      # uit.py:619-635
+    return _factory(6, kwargs)
+
+
+def uit_xxxs(**kwargs):     # uit.py:600-616
+    return _factory(4, kwargs)
+
+
+PRETRAINED_CHECKPOINTS = {   # uit.py:639-655
+    'uit_xs': {'model': uit_xs, 'model_kwargs': dict(outputdim=537, target_length=102),
+               'chkpt': 'https://zenodo.org/record/7690036/files/uit_xs_mAP3409.pt?download=1'},
+    'uit_xxs': {'model': uit_xxs, 'model_kwargs': dict(outputdim=537, target_length=102),
+                'chkpt': 'https://zenodo.org/record/7690036/files/uit_xxs_mAP3221.pt?download=1'},
+    'uit_xxxs': {'model': uit_xxxs, 'model_kwargs': dict(outputdim=537, target_length=102),
+                 'chkpt': 'https://zenodo.org/record/7690036/files/uit_xxxs_mAP3097.pt?download=1'},
+}

@@ -1,0 +1,70 @@
+"""Batch sharding of the hot path across the GPUs of one box (one process per GPU, torch.distributed).
+
+The path is embarrassingly clip-parallel: rank r takes a contiguous slice of the clips, weights are
+replicated.  Two tiny exchanges keep the result identical to a single-GPU call:
+  1. all-reduce(MAX) of ONE 32-bit word -- the bit pattern of the largest mel power -- so that the reference's
+     batch-global top-dB cutoff (Q2) spans the global batch (done inside ``UITBase.forward`` when the model has a
+     ``process_group``);
+  2. all-gather of the ``[B/G, outputdim]`` scores (this module).
+Backend: NCCL over NVLink on the GPUs; the same code runs on gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of ``total`` clips owned by ``rank``; the first ``total % world`` ranks get one more."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def window_shard_bounds(n_windows: int, hop: int, win: int, rank: int, world: int) -> Tuple[int, int, int, int]:
+    """Sliding-window streaming (BASELINE config 5): rank owns windows [w0, w1) and needs the samples
+    [w0*hop, (w1-1)*hop + win) of the stream, i.e. its time range plus a (win - hop) halo."""
+    w0, w1 = shard_bounds(n_windows, rank, world)
+    s0 = w0 * hop
+    s1 = (w1 - 1) * hop + win if w1 > w0 else s0
+    return w0, w1, s0, s1
+
+
+def allreduce_max_word(word: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place MAX of the int32 max-power word.  Non-negative floats order like their bit patterns."""
+    if word.dtype != torch.int32:
+        raise TypeError("the max-power word is the int32 bit pattern of a non-negative float")
+    dist.all_reduce(word, op=dist.ReduceOp.MAX, group=group)
+    return word
+
+
+def gather_scores(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """All-gather per-rank score slices ``[n_r, C]`` (n_r from ``shard_bounds``) into ``[total, C]`` on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} rows, expected {sizes[rank]}")
+    C = local.shape[1]
+    if len(set(sizes)) == 1:
+        out = torch.empty((total, C), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = max(sizes)
+    buf = torch.zeros((pad, C), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    parts: List[torch.Tensor] = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)])
+
+
+def sharded_forward(model, wav_local: torch.Tensor, total: int, group=None, gather: bool = True) -> torch.Tensor:
+    """Run the model on this rank's slice and (optionally) gather all scores.  ``model.process_group`` is set so
+    that the top-dB scope is the global batch."""
+    model.process_group = group if group is not None else dist.group.WORLD
+    local = model(wav_local)
+    return gather_scores(local, total, group) if gather else local
