@@ -122,6 +122,15 @@ UITK_API int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blo
  * (stage 0) or after block i (stage i+1) is left in the workspace at this byte offset after uitk_encoder. */
 UITK_API size_t uitk_encoder_tokens_offset(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length);
 
+/* Tests only: when enabled, the tensor-core encoder also writes the residual stream after the last block
+ * (before the final LayerNorm) to the start of the workspace, like the fp32 path does. */
+UITK_API void uitk_debug_taps(int enable);
+
+/* Tests only: one 128 x N x K tcgen05 GEMM through the library's descriptor / TMEM / bulk-copy plumbing.
+ * d_B_packed is bf16 in the K-major core-matrix layout documented in csrc/tc_ptx.cuh; C (+)= A B^T in fp32. */
+UITK_API int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

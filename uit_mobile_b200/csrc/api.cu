@@ -17,6 +17,8 @@ int check_arch() {
   return UITK_OK;
 }
 
+int g_debug_taps = 0;
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -60,6 +62,8 @@ static int encoder_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, i
 size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
   int64_t rows = 0;
   if (encoder_geometry(cfg, B, T, target_length, &rows) != UITK_OK) return 0;
+  if (cfg->precision == UITK_PREC_BF16)
+    return encoder_tc_workspace_bytes(B * crops_for(T, target_length), rows) + 256;
   return encoder_fp32_workspace_bytes(rows) + 256;
 }
 
@@ -82,10 +86,20 @@ int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const 
   rc = check_arch();
   if (rc != UITK_OK) return rc;
   EncoderArgs a{cfg, d_encoder_blob, d_db, B, T, target_length, eval_avg, d_max_pow, d_probs,
-                d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream)};
+                d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), g_debug_taps};
   if (cfg->precision == UITK_PREC_FP32) return run_encoder_fp32(a);
-  set_error("precision %d not built into this library", cfg->precision);
+  if (cfg->precision == UITK_PREC_BF16) return run_encoder_tc(a);
+  set_error("unknown precision %d", cfg->precision);
   return UITK_EINVAL;
+}
+
+void uitk_debug_taps(int enable) { g_debug_taps = enable; }
+
+int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K, void* stream) {
+  UITK_REQUIRE(d_A && d_B_packed && d_C, UITK_EINVAL, "null pointer");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return run_umma_selftest(d_A, d_B_packed, d_C_init, d_C, N, K, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 }
 
 // One CTA per clip: final LN per token, token mean, head LN, Linear + sigmoid, reduce over crops.
+// POOLED: x already holds the token-mean of the final-LayerNorm output, [B*crops][128] (tensor-core path).
+template <bool POOLED>
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int crops, int tokens,
                                                    const float* __restrict__ norm_w, const float* __restrict__ norm_b,
                                                    const float* __restrict__ hln_w, const float* __restrict__ hln_b,
@@ -229,11 +231,12 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
   float accp[3] = {0.f, 0.f, 0.f};
   if (eval_max) accp[0] = accp[1] = accp[2] = -INFINITY;
   for (int c = 0; c < crops; ++c) {
-    const float* xc = x + (b * crops + c) * (size_t)tokens * 128;
+    const float* xc = x + (b * crops + c) * (size_t)(POOLED ? 1 : tokens) * 128;
     float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (POOLED && warp == 0) ps = *reinterpret_cast<const float4*>(xc + lane * 4);
     const float4 g = *reinterpret_cast<const float4*>(norm_w + lane * 4);
     const float4 be = *reinterpret_cast<const float4*>(norm_b + lane * 4);
-    for (int t = warp; t < tokens; t += 8) {
+    for (int t = warp; t < (POOLED ? 0 : tokens); t += 8) {
       const float4 v = *reinterpret_cast<const float4*>(xc + (size_t)t * 128 + lane * 4);
       float s = v.x + v.y + v.z + v.w;
 #pragma unroll
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
         const float4 t4 = *reinterpret_cast<const float4*>(&part[w][lane * 4]);
         m.x += t4.x; m.y += t4.y; m.z += t4.z; m.w += t4.w;
       }
-      const float invn = 1.f / (float)tokens;
+      const float invn = POOLED ? 1.f : 1.f / (float)tokens;
       m.x *= invn; m.y *= invn; m.z *= invn; m.w *= invn;
       float s = m.x + m.y + m.z + m.w;
 #pragma unroll
@@ -359,10 +362,19 @@ int run_encoder_fp32(const EncoderArgs& a) {
     g.C = x; g.ldc = 128;
     gemm_kernel<128, PRO_PLAIN, EPI_BIAS_RESID><<<dim3(mb, 1), 256, 0, s>>>(g);
   }
-  head_kernel<<<(unsigned)a.B, 256, 0, s>>>(x, crops, tokens, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
+  head_kernel<false><<<(unsigned)a.B, 256, 0, s>>>(x, crops, tokens, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
                                             W + lay.head_wt, W + lay.head_b, cfg.outputdim, lay.outputdim_padded,
                                             a.eval_avg, a.probs);
   count_launches(2 + 5 * cfg.depth);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim,
+                       int eval_max, float* probs, cudaStream_t s) {
+  head_kernel<true><<<(unsigned)B, 256, 0, s>>>(pooled, crops, 1, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
+                                                W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, eval_max, probs);
+  count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;
 }

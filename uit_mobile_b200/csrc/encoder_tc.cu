@@ -1,0 +1,581 @@
+// Tensor-core encoder (UITK_PREC_BF16): ONE persistent megakernel runs patch embed + every transformer block for a
+// tile of 128 token rows (5 clip-crops x 24 tokens) per CTA, with tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
+//
+//   * the fp32 residual stream x[128 x 128] never leaves TENSOR MEMORY (columns 0..127): the proj and fc2 GEMMs
+//     accumulate straight onto it (the residual add is the MMA's accumulate), their biases are deferred into a
+//     running per-column bias vector that the next LayerNorm read adds (packed at load time);
+//   * GEMM accumulators (qkv: 96 columns, fc1 hidden: 384 columns) live in TMEM columns 128..511;
+//   * A operands (LayerNorm output, attention output, ReLU hidden) are produced by the CUDA cores straight from
+//     tcgen05.ld registers into K-major core-matrix shared-memory tiles (thread == row, so every 16-byte store of a
+//     warp is contiguous: no bank conflicts, no swizzle needed);
+//   * weights are pre-packed on the host in exactly that shared-memory layout, so a producer warp streams them
+//     L2 -> SMEM with plain 1-D cp.async.bulk copies through a 3 x 32 KB mbarrier ring (full/empty), overlapping
+//     the LayerNorm / softmax / ReLU work of the 8 compute warps;
+//   * attention (2 heads x 24 x 24 x 16 per clip) stays on the CUDA cores, one thread per (row, head), fp32 softmax.
+// LayerNorm, softmax, residual and all accumulation are fp32; only GEMM operands are rounded to bf16.
+// Reference semantics: models/uit.py:379-396 (features), 89-122 (attention), 181-248 (MLP, block).
+#include "tc_ptx.cuh"
+#include "uitk_common.cuh"
+
+namespace uitk {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 288;          // 8 compute warps + 1 producer warp
+constexpr int kCompute = 256;
+constexpr uint32_t kSlot = 32768;
+constexpr int kSlots = 3;
+constexpr uint32_t kParamFloats = 1280;   // ln1_w ln1_b cb1 qkv_b(128) ln2_w ln2_b cb2 b1(384)
+constexpr uint32_t kParamBytes = kParamFloats * 4 + 8192;   // + Wproj bf16 [4 k8][128][8]
+constexpr uint32_t kQkvBytes = 24576;
+constexpr uint32_t kBlockBytes = kParamBytes + kQkvBytes + 6 * kSlot;
+constexpr uint32_t kPatchBytes = 2 * kSlot;
+
+// shared memory map (bytes)
+constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output); patch: k 0..127
+constexpr uint32_t OFF_U = 32768;                  // 64 KB: H0|H1 (MLP) / A_o + QKV fp32 (attention) / patch k 128..255
+constexpr uint32_t OFF_AO = OFF_U;                 // 8 KB
+constexpr uint32_t OFF_QKV = OFF_U + 8192;         // [128][97] fp32
+constexpr uint32_t OFF_RING = OFF_U + 65536;       // 3 x 32 KB
+constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 13312
+constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 4 x 128 floats
+constexpr uint32_t OFF_BAR = OFF_PART + 4 * 128 * 4;
+constexpr uint32_t kSmemBytes = OFF_BAR + 256;
+constexpr int QKV_LD = 97;
+constexpr int Y_LD = 132;
+
+enum { B_FULLW = 0, B_EMPTYW = 3, B_FULLP = 6, B_EMPTYP = 8, B_ACC = 10, B_X = 11, B_FC1 = 12, B_H = 15, B_COUNT = 17 };
+
+struct TcParams {
+  const unsigned char* wts;     // bf16 section
+  const float* patch_b; const float* time_pos; const float* freq_pos;
+  const float* bn_scale; const float* bn_shift;
+  const float* norm_w; const float* norm_b; const float* cb_final;
+  const float* db; const uint32_t* max_pow;
+  int T, crops, tokens, t_n, target;
+  int RR, G, num_tiles, depth;
+  float* pooled;   // [RR][128]
+  float* dbg_x;    // optional [RR*tokens][128]: residual stream after the last block (pre final LN)
+};
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// wait executed by every thread of a warp: re-converge before the .sync.aligned tcgen05 instructions that follow
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
+}
+
+// LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
+__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, const float* gamma,
+                                              const float* beta, float eps, float* part, unsigned char* dst) {
+  float v[2][32];
+  tmem_ld32(tx + hsel * 64, v[0]);
+  tmem_ld32(tx + hsel * 64 + 32, v[1]);
+  tmem_ld_wait();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v[j][i] += cb[hsel * 64 + j * 32 + i]; s += v[j][i]; }
+  part[hsel * 128 + r] = s;
+  bar_compute();
+  const float mean = (part[r] + part[128 + r]) * (1.f / 128.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v[j][i] -= mean; q = fmaf(v[j][i], v[j][i], q); }
+  part[256 + hsel * 128 + r] = q;
+  bar_compute();
+  const float rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + eps);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = hsel * 64 + j * 32 + c * 8 + i;
+        y[i] = v[j][c * 8 + i] * rstd * gamma[k] + beta[k];
+      }
+      const int k8 = hsel * 8 + j * 4 + c;
+      *reinterpret_cast<uint4*>(dst + k8 * 2048 + r * 16) = pack8_bf16(y);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
+  float* part = reinterpret_cast<float*>(smem + OFF_PART);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // =================================== weight producer =======================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, ps = 0, pphase = 0;
+      auto ring_load = [&](const unsigned char* src, uint32_t bytes) {
+        mbar_wait(&bars[B_EMPTYW + slot], phase ^ 1);
+        mbar_arrive_expect_tx(&bars[B_FULLW + slot], bytes);
+        bulk_g2s(smem + OFF_RING + slot * kSlot, src, bytes, &bars[B_FULLW + slot]);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ring_load(p.wts, kSlot);
+        ring_load(p.wts + kSlot, kSlot);
+        for (int blk = 0; blk < p.depth; ++blk) {
+          const unsigned char* wb = p.wts + kPatchBytes + (size_t)blk * kBlockBytes;
+          mbar_wait(&bars[B_EMPTYP + ps], pphase ^ 1);
+          mbar_arrive_expect_tx(&bars[B_FULLP + ps], kParamBytes);
+          bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
+          if (++ps == 2) { ps = 0; pphase ^= 1; }
+          ring_load(wb + kParamBytes, kQkvBytes);
+          for (int c = 0; c < 6; ++c) ring_load(wb + kParamBytes + kQkvBytes + (size_t)c * kSlot, kSlot);
+        }
+      }
+    }
+  } else {
+    // =================================== compute warps =======================================
+    const int q = warp & 3, hsel = warp >> 2;
+    const int r = q * 32 + lane;                                   // row == TMEM lane
+    const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
+    const uint32_t tacc = tx + 128;                                // accumulator columns 128..511
+    const uint32_t sA = smem_u32(smem + OFF_A), sU = smem_u32(smem + OFF_U), sRing = smem_u32(smem + OFF_RING);
+    constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96);
+
+    uint32_t cslot = 0, cphase = 0;       // ring consumer state (meaningful in thread 0)
+    uint32_t ps = 0, pphase = 0;          // param slot
+    uint32_t ph_acc = 0, ph_x = 0, ph_fc1[3] = {0, 0, 0}, ph_h[2] = {0, 0};
+
+    // issue `ksteps` MMAs consuming the ring slot at the consumer cursor (thread 0 only)
+    auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, int ksteps, bool accum_first) {
+      mbar_wait(&bars[B_FULLW + cslot], cphase);
+      tc_fence_after();
+      const uint32_t b_base = sRing + cslot * kSlot;
+      for (int ks = 0; ks < ksteps; ++ks)
+        umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
+                  (accum_first || ks > 0) ? 1u : 0u);
+      umma_commit(&bars[B_EMPTYW + cslot]);
+      if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
+    };
+
+    const float cutoff = 10.f * log10f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+    const int tokens = p.tokens, t_n = p.t_n;
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int rr0 = tile * p.G;
+      const int g_cnt = min(p.G, p.RR - rr0);
+      const int rows_valid = g_cnt * tokens;
+
+      // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A[128 x 256] ----------------
+      for (int i = tid; i < (128 - rows_valid) * 32; i += kCompute) {      // zero the padding rows
+        const int rz = rows_valid + i / 32, k8 = i % 32;
+        *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
+      }
+      for (int row = warp; row < g_cnt * 64; row += 8) {
+        const int g = row >> 6, mel = row & 63;
+        const int rr = rr0 + g;
+        const int b = rr / p.crops, c = rr - b * p.crops;
+        int start = 0;
+        if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
+        const float* src = p.db + ((size_t)b * 64 + mel) * p.T + start;
+        const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
+        const int rbase = g * tokens + (mel >> 4) * t_n;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int tt = lane + 32 * j;
+          if (tt < 16 * t_n) {
+            const float val = fmaf(fmaxf(__ldg(src + tt), cutoff), sc, sh);
+            const int k = (mel & 15) * 16 + (tt & 15);
+            const int rrow = rbase + (tt >> 4);
+            *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(val);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      bar_compute();
+      if (tid == 0) {
+        tc_fence_after();
+        mma_from_ring(tmem, sA, ID128, 2048, 8, false);
+        mma_from_ring(tmem, sA + 32768, ID128, 2048, 8, true);
+        umma_commit(&bars[B_ACC]);
+      }
+      mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383), written back to TMEM once
+        const int tok = r % tokens, f = tok / t_n, tau = tok - f * t_n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v[32];
+          const int c0 = hsel * 64 + j * 32;
+          tmem_ld32(tx + c0, v);
+          tmem_ld_wait();
+          if (r < rows_valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = (v[i] + __ldg(p.patch_b + c0 + i)) + __ldg(p.time_pos + tau * 128 + c0 + i) + __ldg(p.freq_pos + f * 128 + c0 + i);
+          }
+          tmem_st32(tx + c0, v);
+        }
+        tmem_st_wait();
+      }
+
+      // ---------------- transformer blocks ----------------
+      for (int blk = 0; blk < p.depth; ++blk) {
+        mbar_wait_all(&bars[B_FULLP + ps], pphase);
+        const float* prm = reinterpret_cast<const float*>(smem + OFF_PARAM + ps * kParamBytes);
+        const float *ln1_w = prm, *ln1_b = prm + 128, *cb1 = prm + 256, *qkv_b = prm + 384;
+        const float *ln2_w = prm + 512, *ln2_b = prm + 640, *cb2 = prm + 768, *b1 = prm + 896;
+        const uint32_t sWproj = smem_u32(smem + OFF_PARAM + ps * kParamBytes + kParamFloats * 4);
+
+        // LN1 -> A ; qkv = A Wqkv^T
+        ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        bar_compute();
+        if (tid == 0) {
+          tc_fence_after();
+          mma_from_ring(tmem + 128, sA, ID96, 1536, 8, false);
+          umma_commit(&bars[B_ACC]);
+        }
+        mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
+        tc_fence_after();
+        {   // qkv (+bias) -> fp32 scratch [128][97]
+          float* qkv = reinterpret_cast<float*>(smem + OFF_QKV);
+          float v[32], w[16];
+          tmem_ld32(tacc + hsel * 48, v);
+          tmem_ld16(tacc + hsel * 48 + 32, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) qkv[r * QKV_LD + hsel * 48 + i] = v[i] + qkv_b[hsel * 48 + i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) qkv[r * QKV_LD + hsel * 48 + 32 + i] = w[i] + qkv_b[hsel * 48 + 32 + i];
+        }
+        tc_fence_before();
+        bar_compute();
+        {   // attention: thread = (row, head); softmax((q k^T) * 0.125) v   (uit.py:115-119)
+          const float* qkv = reinterpret_cast<const float*>(smem + OFF_QKV);
+          const int ar = tid & 127, h = tid >> 7;
+          float out[16];
+#pragma unroll
+          for (int d = 0; d < 16; ++d) out[d] = 0.f;
+          if (ar < rows_valid) {
+            const int base = (ar / tokens) * tokens;
+            float qv[16];
+#pragma unroll
+            for (int d = 0; d < 16; ++d) qv[d] = qkv[ar * QKV_LD + h * 16 + d];
+            float sc[UITK_MAX_TOKENS];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+              float a = 0.f;
+              if (j < tokens) {
+                const float* kj = qkv + (base + j) * QKV_LD + 32 + h * 16;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) a = fmaf(qv[d], kj[d], a);
+                a *= 0.125f;
+                mx = fmaxf(mx, a);
+              }
+              sc[j] = a;
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+              sc[j] = j < tokens ? __expf(sc[j] - mx) : 0.f;
+              sum += sc[j];
+            }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+              if (j < tokens) {
+                const float pj = sc[j] * inv;
+                const float* vj = qkv + (base + j) * QKV_LD + 64 + h * 16;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) out[d] = fmaf(pj, vj[d], out[d]);
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 0) * 2048 + ar * 16) = pack8_bf16(out);
+          *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 1) * 2048 + ar * 16) = pack8_bf16(out + 8);
+        }
+        fence_proxy_async_smem();
+        bar_compute();
+        if (tid == 0) {   // x += o Wproj^T   (bias deferred into cb2)
+          tc_fence_after();
+          umma_bf16(tmem, make_smem_desc(sU, 2048, 128), make_smem_desc(sWproj, 2048, 128), ID128, 1u);
+          umma_bf16(tmem, make_smem_desc(sU + 4096, 2048, 128), make_smem_desc(sWproj + 4096, 2048, 128), ID128, 1u);
+          umma_commit(&bars[B_X]);
+        }
+        mbar_wait_all(&bars[B_X], ph_x); ph_x ^= 1;
+        tc_fence_after();
+
+        // LN2 -> A ; hidden = relu(A W1^T + b1) ; x += hidden W2^T
+        ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part, smem + OFF_A);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        bar_compute();
+        if (tid == 0) {
+          tc_fence_after();
+          for (int c = 0; c < 3; ++c) {
+            mma_from_ring(tmem + 128 + c * 128, sA, ID128, 2048, 8, false);
+            umma_commit(&bars[B_FC1 + c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait_all(&bars[B_FC1 + c], ph_fc1[c]); ph_fc1[c] ^= 1;
+          if (c == 2) { mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1; }   // fc2[0] has finished reading H0
+          tc_fence_after();
+          unsigned char* H = smem + OFF_U + (c & 1) * 32768;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[32];
+            tmem_ld32(tacc + c * 128 + hsel * 64 + j * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[cc * 8 + i] + b1[c * 128 + hsel * 64 + j * 32 + cc * 8 + i], 0.f);
+              *reinterpret_cast<uint4*>(H + (hsel * 8 + j * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          bar_compute();
+          if (tid == 0) {
+            tc_fence_after();
+            mma_from_ring(tmem, sU + (c & 1) * 32768, ID128, 2048, 8, true);
+            umma_commit(&bars[B_H + (c & 1)]);
+          }
+        }
+        // block end: fc2[1] (H1) and fc2[2] (H0) complete => x is final for this block, params/H buffers reusable
+        mbar_wait_all(&bars[B_H + 1], ph_h[1]); ph_h[1] ^= 1;
+        mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1;
+        tc_fence_after();
+        if (tid == 0) mbar_arrive(&bars[B_EMPTYP + ps]);
+        if (++ps == 2) { ps = 0; pphase ^= 1; }
+      }
+
+      // ---------------- final LayerNorm (eps 1e-6) + token mean -> pooled[rr][128] ----------------
+      {
+        float* Y = reinterpret_cast<float*>(smem + OFF_A);      // [128][132] fp32 over A + U (both idle now)
+        float v[2][32];
+        tmem_ld32(tx + hsel * 64, v[0]);
+        tmem_ld32(tx + hsel * 64 + 32, v[1]);
+        tmem_ld_wait();
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[j][i] += __ldg(p.cb_final + hsel * 64 + j * 32 + i); s += v[j][i]; }
+        if (p.dbg_x != nullptr && r < rows_valid) {
+          float* dx = p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + hsel * 64;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dx[j * 32 + i] = v[j][i];
+        }
+        part[hsel * 128 + r] = s;
+        bar_compute();
+        const float mean = (part[r] + part[128 + r]) * (1.f / 128.f);
+        float qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[j][i] -= mean; qq = fmaf(v[j][i], v[j][i], qq); }
+        part[256 + hsel * 128 + r] = qq;
+        bar_compute();
+        const float rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + 1e-6f);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int k = hsel * 64 + j * 32 + i;
+            float4 o;
+            o.x = v[j][i + 0] * rstd * __ldg(p.norm_w + k + 0) + __ldg(p.norm_b + k + 0);
+            o.y = v[j][i + 1] * rstd * __ldg(p.norm_w + k + 1) + __ldg(p.norm_b + k + 1);
+            o.z = v[j][i + 2] * rstd * __ldg(p.norm_w + k + 2) + __ldg(p.norm_b + k + 2);
+            o.w = v[j][i + 3] * rstd * __ldg(p.norm_w + k + 3) + __ldg(p.norm_b + k + 3);
+            *reinterpret_cast<float4*>(&Y[r * Y_LD + k]) = o;
+          }
+        tc_fence_before();
+        bar_compute();
+        const int col = tid & 127;
+        const float invn = 1.f / (float)tokens;
+        for (int g = tid >> 7; g < g_cnt; g += 2) {
+          float acc = 0.f;
+          for (int t = 0; t < tokens; ++t) acc += Y[(g * tokens + t) * Y_LD + col];
+          p.pooled[(size_t)(rr0 + g) * 128 + col] = acc * invn;
+        }
+        bar_compute();     // Y (aliases A/U) is free again before the next tile's gather
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// UMMA plumbing self-test: C[128 x N] (+)= A[128 x K] * Bp^T, Bp already packed (bf16, K-major core-matrix layout).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bp,
+                                                               const float* __restrict__ Cinit, float* __restrict__ C, int N, int K) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sAp = smem;                   // up to 128 x 256 bf16 = 64 KB
+  unsigned char* sBp = smem + 65536;           // up to 128 x 256 bf16 = 64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 131072 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hsel = warp >> 2, r = q * 32 + lane;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)N * K * 2;
+    mbar_arrive_expect_tx(&bars[0], bytes);
+    bulk_g2s(sBp, Bp, bytes, &bars[0]);
+  }
+  // A: thread (r, hsel) converts its half of the k-groups
+  const int k8n = K / 8;
+  for (int k8 = hsel; k8 < k8n; k8 += 2) {
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = A[(size_t)r * K + k8 * 8 + i];
+    *reinterpret_cast<uint4*>(sAp + k8 * 2048 + r * 16) = pack8_bf16(y);
+  }
+  if (Cinit != nullptr) {
+    for (int c0 = hsel * 32; c0 < N; c0 += 64) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (c0 + i < N) ? Cinit[(size_t)r * N + c0 + i] : 0.f;
+      tmem_st32(tx + c0, v);
+    }
+    tmem_st_wait();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint32_t lbo_b = (uint32_t)N * 16;
+    for (int ks = 0; ks < K / 16; ++ks)
+      umma_bf16(tmem, make_smem_desc(smem_u32(sAp) + ks * 4096, 2048, 128), make_smem_desc(smem_u32(sBp) + ks * 2 * lbo_b, lbo_b, 128),
+                idesc, (Cinit != nullptr || ks > 0) ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  __syncwarp();
+  tc_fence_after();
+  for (int c0 = hsel * 32; c0 < N; c0 += 64) {
+    float v[32];
+    tmem_ld32(tx + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < N) C[(size_t)r * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+size_t encoder_tc_bf16_section_bytes(int depth) { return (size_t)kPatchBytes + (size_t)depth * kBlockBytes; }
+size_t encoder_tc_param_bytes() { return kParamBytes; }
+size_t encoder_tc_block_bytes() { return kBlockBytes; }
+
+size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows) {
+  return align_up((size_t)rows * 128 * 4, 256) + align_up((size_t)clip_crops * 128 * 4, 256);
+}
+
+int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim, int eval_max,
+                       float* probs, cudaStream_t s);
+
+int run_encoder_tc(const EncoderArgs& a) {
+  const uitk_encoder_cfg& cfg = *a.cfg;
+  const int crops = crops_for(a.T, a.target_length);
+  const int t_n = time_patches_for(a.T, a.target_length);
+  const int tokens = 4 * t_n;
+  const int64_t RR = a.B * crops;
+  UITK_REQUIRE(RR * tokens < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call; chunk the batch");
+  UITK_REQUIRE(t_n <= cfg.grid_t, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
+  const EncoderLayout lay = make_encoder_layout(cfg.depth, cfg.outputdim, cfg.grid_t);
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.blob);
+  const float* W = reinterpret_cast<const float*>(blob + sizeof(BlobHeader));
+  const size_t bf16_off = sizeof(BlobHeader) + align_up(lay.total_floats * sizeof(float), 1024);
+
+  UITK_REQUIRE(encoder_tc_workspace_bytes(RR, RR * tokens) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
+               encoder_tc_workspace_bytes(RR, RR * tokens), a.ws_bytes);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(a.ws);
+  float* dbg_x = reinterpret_cast<float*>(ws);
+  float* pooled = reinterpret_cast<float*>(ws + align_up((size_t)RR * tokens * 128 * 4, 256));
+
+  TcParams p{};
+  p.wts = blob + bf16_off;
+  p.patch_b = W + lay.patch_b; p.time_pos = W + lay.time_pos; p.freq_pos = W + lay.freq_pos;
+  p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift;
+  p.norm_w = W + lay.norm_w; p.norm_b = W + lay.norm_b; p.cb_final = W + lay.cb_final;
+  p.db = a.db; p.max_pow = a.max_pow;
+  p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
+  p.RR = (int)RR; p.G = 128 / tokens; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;
+  p.pooled = pooled;
+  p.dbg_x = a.debug_taps ? dbg_x : nullptr;
+
+  int dev = 0, sms = 0;
+  UITK_CHECK_CUDA(cudaGetDevice(&dev));
+  UITK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  encoder_tc_kernel<<<grid, kThreads, kSmemBytes, a.stream>>>(p);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return launch_head_pooled(pooled, a.B, crops, W, lay, cfg.outputdim, a.eval_avg, a.probs, a.stream);
+}
+
+int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float* C, int N, int K, cudaStream_t s) {
+  UITK_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, UITK_EINVAL, "selftest: bad N/K");
+  const int smem = 131072 + 256;
+  UITK_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_selftest_kernel<<<1, 256, smem, s>>>(A, reinterpret_cast<const unsigned char*>(Bp), Cinit, C, N, K);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+}  // namespace uitk

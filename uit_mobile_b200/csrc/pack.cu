@@ -40,6 +40,7 @@ EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
   l.time_pos = take(cur, (size_t)grid_t * 128); l.freq_pos = take(cur, 4 * 128);
   l.norm_w = take(cur, 128); l.norm_b = take(cur, 128);
   l.hln_w = take(cur, 128); l.hln_b = take(cur, 128);
+  l.cb_final = take(cur, 128);
   l.head_wt = take(cur, (size_t)128 * l.outputdim_padded); l.head_b = take(cur, l.outputdim_padded);
   l.blocks = cur;
   size_t b = 0;
@@ -71,6 +72,24 @@ static void transpose_into(float* dst, const float* w, int out_f, int in_f, int 
   for (int o = 0; o < out_f; ++o)
     for (int k = 0; k < in_f; ++k) dst[(size_t)k * ld_dst + o] = w[(size_t)o * in_f + k];
 }
+
+// fp32 -> bf16 bits, round to nearest even (matches __float2bfloat16_rn for finite values)
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// W[(n0+n)*ldw + k0+k], n<N, k<K  ->  K-major core-matrix layout: dst[((k/8)*N + n)*8 + k%8]   (tc_ptx.cuh)
+static void pack_kmajor(uint16_t* dst, const float* W, int ldw, int n0, int N, int k0, int K) {
+  for (int k8 = 0; k8 < K / 8; ++k8)
+    for (int n = 0; n < N; ++n)
+      for (int i = 0; i < 8; ++i) dst[((size_t)k8 * N + n) * 8 + i] = f2bf(W[(size_t)(n0 + n) * ldw + k0 + k8 * 8 + i]);
+}
+
+static size_t fp32_section_bytes(const EncoderLayout& l) { return (l.total_floats * sizeof(float) + 1023) / 1024 * 1024; }
 
 }  // namespace uitk
 
@@ -139,7 +158,9 @@ static int check_cfg(const uitk_encoder_cfg* cfg) {
 size_t uitk_encoder_blob_bytes(const uitk_encoder_cfg* cfg) {
   if (check_cfg(cfg) != UITK_OK) return 0;
   const EncoderLayout l = make_encoder_layout(cfg->depth, cfg->outputdim, cfg->grid_t);
-  return sizeof(BlobHeader) + l.total_floats * sizeof(float);
+  size_t n = sizeof(BlobHeader) + fp32_section_bytes(l);
+  if (cfg->precision == UITK_PREC_BF16) n += encoder_tc_bf16_section_bytes(cfg->depth);
+  return n;
 }
 
 int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* h_blob, size_t blob_bytes) {
@@ -185,6 +206,36 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     transpose_into(Wb + l.blk.fc1_wt, b[8], 384, 128, 384); memcpy(Wb + l.blk.fc1_b, b[9], 384 * 4);
     transpose_into(Wb + l.blk.fc2_wt, b[10], 128, 384, 128); memcpy(Wb + l.blk.fc2_b, b[11], 128 * 4);
   }
+  // deferred-bias vectors of the tensor-core path: cb1(i) = sum_{j<i} (proj_b_j + fc2_b_j), cb2(i) = cb1(i) + proj_b_i
+  std::vector<float> cb(128, 0.f);
+  unsigned char* sec = reinterpret_cast<unsigned char*>(h_blob) + sizeof(BlobHeader) + fp32_section_bytes(l);
+  if (cfg->precision == UITK_PREC_BF16) {
+    hdr->bf16_offset = sizeof(BlobHeader) + fp32_section_bytes(l);
+    pack_kmajor(reinterpret_cast<uint16_t*>(sec), t[4], 256, 0, 128, 0, 128);              // patch, k 0..127
+    pack_kmajor(reinterpret_cast<uint16_t*>(sec + 32768), t[4], 256, 0, 128, 128, 128);    // patch, k 128..255
+  }
+  for (int i = 0; i < cfg->depth; ++i) {
+    const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
+    if (cfg->precision == UITK_PREC_BF16) {
+      unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();
+      float* prm = reinterpret_cast<float*>(blk);
+      memcpy(prm + 0, b[0], 128 * 4); memcpy(prm + 128, b[1], 128 * 4);        // ln1 w, b
+      memcpy(prm + 256, cb.data(), 128 * 4);                                   // cb1
+      memcpy(prm + 384, b[3], 96 * 4);                                         // qkv bias (padded to 128)
+      memcpy(prm + 512, b[6], 128 * 4); memcpy(prm + 640, b[7], 128 * 4);      // ln2 w, b
+      for (int c = 0; c < 128; ++c) prm[768 + c] = cb[c] + b[5][c];            // cb2 = cb1 + proj bias
+      memcpy(prm + 896, b[9], 384 * 4);                                        // fc1 bias
+      uint16_t* w = reinterpret_cast<uint16_t*>(blk + 1280 * 4);
+      pack_kmajor(w, b[4], 32, 0, 128, 0, 32);                                 // Wproj [128][32]
+      w = reinterpret_cast<uint16_t*>(blk + encoder_tc_param_bytes());
+      pack_kmajor(w, b[2], 128, 0, 96, 0, 128);                                // Wqkv [96][128]
+      w += 96 * 128;
+      for (int c = 0; c < 3; ++c) { pack_kmajor(w, b[8], 128, c * 128, 128, 0, 128); w += 128 * 128; }    // W1 rows c*128..
+      for (int c = 0; c < 3; ++c) { pack_kmajor(w, b[10], 384, 0, 128, c * 128, 128); w += 128 * 128; }   // W2 k-slice c
+    }
+    for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
+  }
+  memcpy(W + l.cb_final, cb.data(), 128 * 4);
   return UITK_OK;
 }
 

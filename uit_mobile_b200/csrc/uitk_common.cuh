@@ -62,6 +62,7 @@ struct EncoderLayout {
   size_t patch_wt, patch_b;           // [256][128], [128]
   size_t time_pos, freq_pos;          // [grid_t][128], [4][128]
   size_t norm_w, norm_b, hln_w, hln_b;
+  size_t cb_final;                    // [128] sum of all deferred proj/fc2 biases (tensor-core path)
   size_t head_wt, head_b;             // [128][outputdim_padded], [outputdim_padded]
   int outputdim_padded;
   size_t blocks;                      // first block
@@ -107,8 +108,15 @@ struct EncoderArgs {
   void* ws;
   size_t ws_bytes;
   cudaStream_t stream;
+  int debug_taps;
 };
 int run_encoder_fp32(const EncoderArgs& a);
+int run_encoder_tc(const EncoderArgs& a);
+int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float* C, int N, int K, cudaStream_t s);
+size_t encoder_tc_bf16_section_bytes(int depth);
+size_t encoder_tc_param_bytes();
+size_t encoder_tc_block_bytes();
+size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows);
 size_t encoder_fp32_workspace_bytes(int64_t rows);   // rows = B * crops * tokens
 
 }  // namespace uitk
