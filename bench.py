@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--arch", choices=list(ENCODER_FLOPS), default="uit_xs")
     ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
-    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("UITK_PRECISION", "fp32"))
+    ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("UITK_PRECISION", "bf16"))
     ap.add_argument("--chunk", type=int, default=512, help="host pipeline chunk (clips)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -113,7 +113,7 @@ def test_fp32_encoder_block_trace(depth):
     sub = {k: v for k, v in sd.items() if not k.startswith("blocks.") or int(k.split(".")[1]) < depth}
     m = U.models.UITBase(outputdim=537, target_length=102, patch_size=16, embed_dim=128, depth=depth, num_heads=2,
                          mlp_ratio=3.0, pooling="mean", init_bn=True, act_layer=torch.nn.ReLU,
-                         attention_type="BNeckAttention")
+                         attention_type="BNeckAttention", precision="fp32")
     m.load_state_dict(sub, strict=True)
     m = m.to(DEV).eval()
     x = torch.from_numpy(INPUTS["noise"][:2]).to(DEV)

@@ -218,7 +218,7 @@ class UITBase(nn.Module):
                  norm_layer=None, act_layer=None, init_values=None, target_length=1012, pooling='token',
                  wavtransforms=None, spectransforms=None, time_patch_out: Optional[float] = None,
                  freq_patch_out: Optional[float] = None, block_type='Block', attention_type='Attention',
-                 eval_avg='mean', precision: str = "fp32", process_group=None, **kwargs):
+                 eval_avg='mean', precision: str = "bf16", process_group=None, **kwargs):
         super().__init__()
         assert pooling in ('mean', 'token', 'dm')
         self.outputdim, self.pooling, self.embed_dim = outputdim, pooling, embed_dim
