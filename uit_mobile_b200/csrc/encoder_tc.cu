@@ -37,13 +37,13 @@ constexpr uint32_t kPatchBytes = 2 * kSlot;
 constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output); patch: k 0..127
 constexpr uint32_t OFF_U = 32768;                  // 64 KB: H0|H1 (MLP) / A_o + QKV fp32 (attention) / patch k 128..255
 constexpr uint32_t OFF_AO = OFF_U;                 // 8 KB
-constexpr uint32_t OFF_QKV = OFF_U + 8192;         // [128][97] fp32
+constexpr uint32_t OFF_QKV = OFF_U + 8192;         // [128][100] fp32
 constexpr uint32_t OFF_RING = OFF_U + 65536;       // 3 x 32 KB
 constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 13312
 constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 4 x 128 floats
 constexpr uint32_t OFF_BAR = OFF_PART + 4 * 128 * 4;
 constexpr uint32_t kSmemBytes = OFF_BAR + 256;
-constexpr int QKV_LD = 97;
+constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr int Y_LD = 132;
 
 enum { B_FULLW = 0, B_EMPTYW = 3, B_FULLP = 6, B_EMPTYP = 8, B_ACC = 10, B_X = 11, B_FC1 = 12, B_H = 15, B_COUNT = 17 };
@@ -78,7 +78,11 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
 #pragma unroll
   for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { v[j][i] += cb[hsel * 64 + j * 32 + i]; s += v[j][i]; }
+    for (int i = 0; i < 32; i += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
+      v[j][i] += c4.x; v[j][i + 1] += c4.y; v[j][i + 2] += c4.z; v[j][i + 3] += c4.w;
+      s += (v[j][i] + v[j][i + 1]) + (v[j][i + 2] + v[j][i + 3]);
+    }
   part[hsel * 128 + r] = s;
   bar_compute();
   const float mean = (part[r] + part[128 + r]) * (1.f / 128.f);
@@ -95,11 +99,13 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float y[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = hsel * 64 + j * 32 + c * 8 + i;
-        y[i] = v[j][c * 8 + i] * rstd * gamma[k] + beta[k];
-      }
+      const int k0 = hsel * 64 + j * 32 + c * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + k0), g1 = *reinterpret_cast<const float4*>(gamma + k0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + k0), b1v = *reinterpret_cast<const float4*>(beta + k0 + 4);
+      y[0] = v[j][c * 8 + 0] * rstd * g0.x + b0.x; y[1] = v[j][c * 8 + 1] * rstd * g0.y + b0.y;
+      y[2] = v[j][c * 8 + 2] * rstd * g0.z + b0.z; y[3] = v[j][c * 8 + 3] * rstd * g0.w + b0.w;
+      y[4] = v[j][c * 8 + 4] * rstd * g1.x + b1v.x; y[5] = v[j][c * 8 + 5] * rstd * g1.y + b1v.y;
+      y[6] = v[j][c * 8 + 6] * rstd * g1.z + b1v.z; y[7] = v[j][c * 8 + 7] * rstd * g1.w + b1v.w;
       const int k8 = hsel * 8 + j * 4 + c;
       *reinterpret_cast<uint4*>(dst + k8 * 2048 + r * 16) = pack8_bf16(y);
     }
@@ -146,7 +152,11 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
           bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
           if (++ps == 2) { ps = 0; pphase ^= 1; }
           ring_load(wb + kParamBytes, kQkvBytes);
-          for (int c = 0; c < 6; ++c) ring_load(wb + kParamBytes + kQkvBytes + (size_t)c * kSlot, kSlot);
+          // consumption order: fc1[0] fc1[1] fc2[0] fc1[2] fc2[1] fc2[2]   (blob order: W1_0..2, W2_0..2)
+          const unsigned char* w1 = wb + kParamBytes + kQkvBytes;
+          const unsigned char* w2 = w1 + 3 * (size_t)kSlot;
+          ring_load(w1, kSlot); ring_load(w1 + kSlot, kSlot); ring_load(w2, kSlot);
+          ring_load(w1 + 2 * (size_t)kSlot, kSlot); ring_load(w2 + kSlot, kSlot); ring_load(w2 + 2 * (size_t)kSlot, kSlot);
         }
       }
     }
@@ -188,23 +198,42 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         const int rz = rows_valid + i / 32, k8 = i % 32;
         *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
       }
-      for (int row = warp; row < g_cnt * 64; row += 8) {
-        const int g = row >> 6, mel = row & 63;
-        const int rr = rr0 + g;
-        const int b = rr / p.crops, c = rr - b * p.crops;
-        int start = 0;
-        if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
-        const float* src = p.db + ((size_t)b * 64 + mel) * p.T + start;
-        const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
-        const int rbase = g * tokens + (mel >> 4) * t_n;
+      for (int row0 = warp; row0 < g_cnt * 64; row0 += 32) {      // 4 rows (12 loads) in flight per warp
+        float val[4][3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int tt = lane + 32 * j;
-          if (tt < 16 * t_n) {
-            const float val = fmaf(fmaxf(__ldg(src + tt), cutoff), sc, sh);
-            const int k = (mel & 15) * 16 + (tt & 15);
-            const int rrow = rbase + (tt >> 4);
-            *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(val);
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + 8 * u;
+          if (row < g_cnt * 64) {
+            const int g = row >> 6, mel = row & 63;
+            const int rr = rr0 + g;
+            const int b = rr / p.crops, c = rr - b * p.crops;
+            int start = 0;
+            if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
+            const float* src = p.db + ((size_t)b * 64 + mel) * p.T + start;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int tt = lane + 32 * j;
+              val[u][j] = tt < 16 * t_n ? __ldg(src + tt) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + 8 * u;
+          if (row < g_cnt * 64) {
+            const int g = row >> 6, mel = row & 63;
+            const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
+            const int rbase = g * tokens + (mel >> 4) * t_n;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int tt = lane + 32 * j;
+              if (tt < 16 * t_n) {
+                const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
+                const int k = (mel & 15) * 16 + (tt & 15);
+                const int rrow = rbase + (tt >> 4);
+                *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
+              }
+            }
           }
         }
       }
@@ -263,10 +292,18 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
           tmem_ld32(tacc + hsel * 48, v);
           tmem_ld16(tacc + hsel * 48 + 32, w);
           tmem_ld_wait();
+          float* dstq = qkv + r * QKV_LD + hsel * 48;
+          const float* bq = qkv_b + hsel * 48;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) qkv[r * QKV_LD + hsel * 48 + i] = v[i] + qkv_b[hsel * 48 + i];
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
+            *reinterpret_cast<float4*>(dstq + i) = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) qkv[r * QKV_LD + hsel * 48 + 32 + i] = w[i] + qkv_b[hsel * 48 + 32 + i];
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bq + 32 + i);
+            *reinterpret_cast<float4*>(dstq + 32 + i) = make_float4(w[i] + b4.x, w[i + 1] + b4.y, w[i + 2] + b4.z, w[i + 3] + b4.w);
+          }
         }
         tc_fence_before();
         bar_compute();
@@ -280,16 +317,23 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
             const int base = (ar / tokens) * tokens;
             float qv[16];
 #pragma unroll
-            for (int d = 0; d < 16; ++d) qv[d] = qkv[ar * QKV_LD + h * 16 + d];
+            for (int d = 0; d < 16; d += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(qkv + ar * QKV_LD + h * 16 + d);
+              qv[d] = t4.x; qv[d + 1] = t4.y; qv[d + 2] = t4.z; qv[d + 3] = t4.w;
+            }
             float sc[UITK_MAX_TOKENS];
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
               float a = 0.f;
               if (j < tokens) {
-                const float* kj = qkv + (base + j) * QKV_LD + 32 + h * 16;
+                const float4* kj = reinterpret_cast<const float4*>(qkv + (base + j) * QKV_LD + 32 + h * 16);
 #pragma unroll
-                for (int d = 0; d < 16; ++d) a = fmaf(qv[d], kj[d], a);
+                for (int d = 0; d < 4; ++d) {
+                  const float4 k4 = kj[d];
+                  a = fmaf(qv[4 * d], k4.x, a); a = fmaf(qv[4 * d + 1], k4.y, a);
+                  a = fmaf(qv[4 * d + 2], k4.z, a); a = fmaf(qv[4 * d + 3], k4.w, a);
+                }
                 a *= 0.125f;
                 mx = fmaxf(mx, a);
               }
@@ -306,9 +350,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
             for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
               if (j < tokens) {
                 const float pj = sc[j] * inv;
-                const float* vj = qkv + (base + j) * QKV_LD + 64 + h * 16;
+                const float4* vj = reinterpret_cast<const float4*>(qkv + (base + j) * QKV_LD + 64 + h * 16);
 #pragma unroll
-                for (int d = 0; d < 16; ++d) out[d] = fmaf(pj, vj[d], out[d]);
+                for (int d = 0; d < 4; ++d) {
+                  const float4 v4 = vj[d];
+                  out[4 * d] = fmaf(pj, v4.x, out[4 * d]); out[4 * d + 1] = fmaf(pj, v4.y, out[4 * d + 1]);
+                  out[4 * d + 2] = fmaf(pj, v4.z, out[4 * d + 2]); out[4 * d + 3] = fmaf(pj, v4.w, out[4 * d + 3]);
+                }
               }
             }
           }
@@ -333,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         bar_compute();
         if (tid == 0) {
           tc_fence_after();
-          for (int c = 0; c < 3; ++c) {
+          for (int c = 0; c < 2; ++c) {
             mma_from_ring(tmem + 128 + c * 128, sA, ID128, 2048, 8, false);
             umma_commit(&bars[B_FC1 + c]);
           }
@@ -352,8 +400,12 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               float y[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[cc * 8 + i] + b1[c * 128 + hsel * 64 + j * 32 + cc * 8 + i], 0.f);
+              const float* bb = b1 + c * 128 + hsel * 64 + j * 32 + cc * 8;
+              const float4 ba = *reinterpret_cast<const float4*>(bb), bc = *reinterpret_cast<const float4*>(bb + 4);
+              y[0] = fmaxf(v[cc * 8 + 0] + ba.x, 0.f); y[1] = fmaxf(v[cc * 8 + 1] + ba.y, 0.f);
+              y[2] = fmaxf(v[cc * 8 + 2] + ba.z, 0.f); y[3] = fmaxf(v[cc * 8 + 3] + ba.w, 0.f);
+              y[4] = fmaxf(v[cc * 8 + 4] + bc.x, 0.f); y[5] = fmaxf(v[cc * 8 + 5] + bc.y, 0.f);
+              y[6] = fmaxf(v[cc * 8 + 6] + bc.z, 0.f); y[7] = fmaxf(v[cc * 8 + 7] + bc.w, 0.f);
               *reinterpret_cast<uint4*>(H + (hsel * 8 + j * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
             }
           }
@@ -364,6 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
             tc_fence_after();
             mma_from_ring(tmem, sU + (c & 1) * 32768, ID128, 2048, 8, true);
             umma_commit(&bars[B_H + (c & 1)]);
+            if (c == 0) {   // fc1[2] goes behind fc2[0] so that its weights had a ring slot to land in
+              mma_from_ring(tmem + 128 + 2 * 128, sA, ID128, 2048, 8, false);
+              umma_commit(&bars[B_FC1 + 2]);
+            }
           }
         }
         // block end: fc2[1] (H1) and fc2[2] (H0) complete => x is final for this block, params/H buffers reusable

@@ -21,7 +21,8 @@ constexpr int kFramesPerRound = 16;
 constexpr int kRounds = 7;
 constexpr int kChunk = kFramesPerRound * kRounds;                              // 112 frames / CTA
 constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT;  // 2912
-constexpr int kExStride = 272;                                                 // float2 per frame group (16 x 17)
+constexpr int kExStride = 280;   // float2 per frame group: 16 x 17 used; 560 words = 16 mod 32 so that the two
+                                 // frame groups of a warp use complementary banks for 32-bit accesses
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -130,7 +131,7 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
     }
     fft16(v);                                   // over m -> k1
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], S.tw256[j * k1]);
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], S.tw256[k1 * 16 + j]);
     float2* e = S.ex + g * kExStride;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + j] = v[k1];

@@ -116,7 +116,10 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
   memcpy(fb->window, h_window, sizeof(float) * 512);
   const double two_pi = 6.283185307179586476925286766559;
   for (int j = 0; j < 256; ++j) {
-    fb->tw256[j] = make_float2((float)cos(two_pi * j / 256.0), (float)-sin(two_pi * j / 256.0));
+    // tw256 is stored as the table the kernel indexes: entry [k1*16 + lane] = exp(-2*pi*i*lane*k1/256), so that the
+    // 16 lanes of a frame group read 16 consecutive entries (bank-conflict free)
+    const int k1 = j >> 4, ln = j & 15;
+    fb->tw256[j] = make_float2((float)cos(two_pi * (ln * k1) / 256.0), (float)-sin(two_pi * (ln * k1) / 256.0));
     fb->tw512[j] = make_float2((float)cos(two_pi * j / 512.0), (float)-sin(two_pi * j / 512.0));
   }
   int n = 0;

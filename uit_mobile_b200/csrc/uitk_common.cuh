@@ -39,7 +39,7 @@ struct FrontendBlob {
   int n_weights;             // packed filterbank entries
   int pad0, pad1;
   float window[512];         // front_end.0.spectrogram.window
-  float2 tw256[256];         // exp(-2*pi*i*j/256)
+  float2 tw256[256];         // [k1*16 + lane] = exp(-2*pi*i*lane*k1/256)
   float2 tw512[256];         // exp(-2*pi*i*k/512)
   int mel_lo[64];            // first frequency bin with a non-zero weight for mel bin m
   int mel_cnt[64];           // number of consecutive bins
