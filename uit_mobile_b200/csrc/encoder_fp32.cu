@@ -370,10 +370,91 @@ int run_encoder_fp32(const EncoderArgs& a) {
   return UITK_OK;
 }
 
+// Head for the tensor-core path: pooled features [B*crops][128] -> head LayerNorm(1e-5) -> Linear -> sigmoid -> crop
+// mean/max.  8 clips per CTA so that every head-weight element fetched from L2 feeds 8 FMAs.
+namespace {
+constexpr int kHeadClips = 8;
+__global__ void __launch_bounds__(256) head_pooled_kernel(const float* __restrict__ pooled, long long B, int crops,
+                                                          const float* __restrict__ hln_w, const float* __restrict__ hln_b,
+                                                          const float* __restrict__ head_wt, const float* __restrict__ head_b,
+                                                          int outputdim, int ld_head, int eval_max, float* __restrict__ probs) {
+  __shared__ __align__(16) float pn[kHeadClips][128];      // normalised features
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b0 = (long long)blockIdx.x * kHeadClips;
+  float accp[3][kHeadClips];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < kHeadClips; ++c) accp[r][c] = eval_max ? -INFINITY : 0.f;
+  const float4 hg = *reinterpret_cast<const float4*>(hln_w + lane * 4);
+  const float4 hb = *reinterpret_cast<const float4*>(hln_b + lane * 4);
+  for (int c = 0; c < crops; ++c) {
+    __syncthreads();
+    {   // warp w normalises clip b0 + w
+      const long long b = b0 + warp;
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B) m = *reinterpret_cast<const float4*>(pooled + (b * crops + c) * 128 + lane * 4);
+      float s = m.x + m.y + m.z + m.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / 128.f);
+      const float d0 = m.x - mean, d1 = m.y - mean, d2 = m.z - mean, d3 = m.w - mean;
+      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
+      *reinterpret_cast<float4*>(&pn[warp][lane * 4]) =
+          make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
+    }
+    __syncthreads();
+    float z[3][kHeadClips];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int oidx = tid + 256 * r;
+      const float bias = oidx < outputdim ? head_b[oidx] : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < kHeadClips; ++cc) z[r][cc] = bias;
+    }
+    for (int k = 0; k < 128; k += 4) {
+      float4 pv[kHeadClips];
+#pragma unroll
+      for (int cc = 0; cc < kHeadClips; ++cc) pv[cc] = *reinterpret_cast<const float4*>(&pn[cc][k]);   // broadcast loads
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int oidx = tid + 256 * r;
+        if (oidx < outputdim) {
+          const float w0 = __ldg(head_wt + (size_t)(k + 0) * ld_head + oidx), w1 = __ldg(head_wt + (size_t)(k + 1) * ld_head + oidx);
+          const float w2 = __ldg(head_wt + (size_t)(k + 2) * ld_head + oidx), w3 = __ldg(head_wt + (size_t)(k + 3) * ld_head + oidx);
+#pragma unroll
+          for (int cc = 0; cc < kHeadClips; ++cc)
+            z[r][cc] = fmaf(pv[cc].w, w3, fmaf(pv[cc].z, w2, fmaf(pv[cc].y, w1, fmaf(pv[cc].x, w0, z[r][cc]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < kHeadClips; ++cc) {
+        const float pr = 1.f / (1.f + expf(-z[r][cc]));
+        accp[r][cc] = eval_max ? fmaxf(accp[r][cc], pr) : accp[r][cc] + pr;
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int oidx = tid + 256 * r;
+    if (oidx >= outputdim) continue;
+#pragma unroll
+    for (int cc = 0; cc < kHeadClips; ++cc)
+      if (b0 + cc < B) probs[(b0 + cc) * outputdim + oidx] = eval_max ? accp[r][cc] : accp[r][cc] / (float)crops;
+  }
+}
+}  // namespace
+
 int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim,
                        int eval_max, float* probs, cudaStream_t s) {
-  head_kernel<true><<<(unsigned)B, 256, 0, s>>>(pooled, crops, 1, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
-                                                W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, eval_max, probs);
+  head_pooled_kernel<<<(unsigned)((B + kHeadClips - 1) / kHeadClips), 256, 0, s>>>(
+      pooled, (long long)B, crops, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded,
+      eval_max, probs);
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;

@@ -1,16 +1,19 @@
 // Tensor-core encoder (UITK_PREC_BF16): ONE persistent megakernel runs patch embed + every transformer block for a
 // tile of 128 token rows (5 clip-crops x 24 tokens) per CTA, with tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
+// TWO CTAs are resident per SM (<= 112 regs/thread, 108 KB SMEM, 256 TMEM columns each) so that one CTA's
+// LayerNorm / softmax / ReLU work on the CUDA cores overlaps the other CTA's MMAs and weight streaming.
 //
 //   * the fp32 residual stream x[128 x 128] never leaves TENSOR MEMORY (columns 0..127): the proj and fc2 GEMMs
 //     accumulate straight onto it (the residual add is the MMA's accumulate), their biases are deferred into a
 //     running per-column bias vector that the next LayerNorm read adds (packed at load time);
-//   * GEMM accumulators (qkv: 96 columns, fc1 hidden: 384 columns) live in TMEM columns 128..511;
+//   * GEMM accumulators (qkv: 96 columns; fc1 hidden: 2 x 64-column chunks, double buffered) live in columns 128..255;
 //   * A operands (LayerNorm output, attention output, ReLU hidden) are produced by the CUDA cores straight from
 //     tcgen05.ld registers into K-major core-matrix shared-memory tiles (thread == row, so every 16-byte store of a
 //     warp is contiguous: no bank conflicts, no swizzle needed);
-//   * weights are pre-packed on the host in exactly that shared-memory layout, so a producer warp streams them
-//     L2 -> SMEM with plain 1-D cp.async.bulk copies through a 3 x 32 KB mbarrier ring (full/empty), overlapping
-//     the LayerNorm / softmax / ReLU work of the 8 compute warps;
+//   * weights are pre-packed on the host in exactly that shared-memory layout and in consumption order, so a
+//     producer warp streams them L2 -> SMEM with plain 1-D cp.async.bulk copies through a 2 x 16 KB mbarrier ring
+//     (full/empty, slots released by tcgen05.commit); the MLP runs as 6 hidden chunks of 64 columns with fc1 of
+//     chunk c+2 issued behind fc2 of chunk c, so ReLU epilogues overlap MMAs;
 //   * attention (2 heads x 24 x 24 x 16 per clip) stays on the CUDA cores, one thread per (row, head), fp32 softmax.
 // LayerNorm, softmax, residual and all accumulation are fp32; only GEMM operands are rounded to bf16.
 // Reference semantics: models/uit.py:379-396 (features), 89-122 (attention), 181-248 (MLP, block).
@@ -25,28 +28,29 @@ using namespace tc;
 
 constexpr int kThreads = 288;          // 8 compute warps + 1 producer warp
 constexpr int kCompute = 256;
-constexpr uint32_t kSlot = 32768;
-constexpr int kSlots = 3;
-constexpr uint32_t kParamFloats = 1280;   // ln1_w ln1_b cb1 qkv_b(128) ln2_w ln2_b cb2 b1(384)
-constexpr uint32_t kParamBytes = kParamFloats * 4 + 8192;   // + Wproj bf16 [4 k8][128][8]
-constexpr uint32_t kQkvBytes = 24576;
-constexpr uint32_t kBlockBytes = kParamBytes + kQkvBytes + 6 * kSlot;
-constexpr uint32_t kPatchBytes = 2 * kSlot;
+constexpr uint32_t kSlot = 16384;
+constexpr int kSlots = 2;
+constexpr uint32_t kParamFloats = 1280;               // ln1_w ln1_b cb1 qkv_b(128) ln2_w ln2_b cb2 b1(384)
+constexpr uint32_t kParamBytes = kParamFloats * 4;    // 5120
+constexpr uint32_t kQkvHalfBytes = 96 * 64 * 2;       // Wqkv, one K half: 12288
+constexpr uint32_t kProjBytes = 128 * 32 * 2;         // 8192
+constexpr uint32_t kBlockBytes = kParamBytes + 2 * kQkvHalfBytes + kProjBytes + 12 * kSlot;   // 234496
+constexpr uint32_t kPatchBytes = 4 * kSlot;           // 4 K-quarters of the patch weight
 
-// shared memory map (bytes)
-constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output); patch: k 0..127
-constexpr uint32_t OFF_U = 32768;                  // 64 KB: H0|H1 (MLP) / A_o + QKV fp32 (attention) / patch k 128..255
-constexpr uint32_t OFF_AO = OFF_U;                 // 8 KB
-constexpr uint32_t OFF_QKV = OFF_U + 8192;         // [128][100] fp32
-constexpr uint32_t OFF_RING = OFF_U + 65536;       // 3 x 32 KB
-constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 13312
+// shared memory map (bytes); one CTA uses 108.3 KB so that two fit on an SM
+constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output) | patch k 0..127 | attention scratch
+constexpr uint32_t OFF_H = 32768;                  // 2 x 16 KB hidden chunks     | patch k 128..255 | attention scratch
+constexpr uint32_t OFF_AO = OFF_A;                 // 8 KB attention output operand [128 x 32]
+constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 = 51200 B (ends inside H)
+constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
+constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 5120
 constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 4 x 128 floats
 constexpr uint32_t OFF_BAR = OFF_PART + 4 * 128 * 4;
 constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
-constexpr int Y_LD = 132;
+constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = 3, B_FULLP = 6, B_EMPTYP = 8, B_ACC = 10, B_X = 11, B_FC1 = 12, B_H = 15, B_COUNT = 17 };
+enum { B_FULLW = 0, B_EMPTYW = 2, B_FULLP = 4, B_EMPTYP = 6, B_ACC = 8, B_X = 9, B_FC1 = 10, B_H = 12, B_COUNT = 14 };
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
@@ -67,51 +71,73 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 }
 
-// LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
-__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, const float* gamma,
-                                              const float* beta, float eps, float* part, unsigned char* dst) {
-  float v[2][32];
-  tmem_ld32(tx + hsel * 64, v[0]);
-  tmem_ld32(tx + hsel * 64 + 32, v[1]);
-  tmem_ld_wait();
+// Row statistics of (x + cb) for this thread's row; the two threads of a row (hsel 0/1) each reduce 64 columns and
+// exchange partial sums through `part`.  Three cheap passes over TMEM keep the live register count at 32 values.
+__device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part, float& mean,
+                                          float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < 2; ++j) {
+    float v[32];
+    tmem_ld32(tx + hsel * 64 + j * 32, v);
+    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
-      v[j][i] += c4.x; v[j][i + 1] += c4.y; v[j][i + 2] += c4.z; v[j][i + 3] += c4.w;
-      s += (v[j][i] + v[j][i + 1]) + (v[j][i + 2] + v[j][i + 3]);
+      s += ((v[i] + c4.x) + (v[i + 1] + c4.y)) + ((v[i + 2] + c4.z) + (v[i + 3] + c4.w));
     }
+  }
   part[hsel * 128 + r] = s;
   bar_compute();
-  const float mean = (part[r] + part[128 + r]) * (1.f / 128.f);
+  mean = (part[r] + part[128 + r]) * (1.f / 128.f);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < 2; ++j) {
+    float v[32];
+    tmem_ld32(tx + hsel * 64 + j * 32, v);
+    tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { v[j][i] -= mean; q = fmaf(v[j][i], v[j][i], q); }
+    for (int i = 0; i < 32; i += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
+      const float d0 = v[i] + c4.x - mean, d1 = v[i + 1] + c4.y - mean, d2 = v[i + 2] + c4.z - mean, d3 = v[i + 3] + c4.w - mean;
+      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+    }
+  }
   part[256 + hsel * 128 + r] = q;
   bar_compute();
-  const float rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + eps);
+  rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + eps);
+}
+
+// LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
+__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, const float* gamma,
+                                              const float* beta, float eps, float* part, unsigned char* dst) {
+  float mean, rstd;
+  row_stats(tx, hsel, r, cb, eps, part, mean, rstd);
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < 2; ++j) {
+    float v[32];
+    tmem_ld32(tx + hsel * 64 + j * 32, v);
+    tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float y[8];
       const int k0 = hsel * 64 + j * 32 + c * 8;
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + k0), g1 = *reinterpret_cast<const float4*>(gamma + k0 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + k0), b1v = *reinterpret_cast<const float4*>(beta + k0 + 4);
-      y[0] = v[j][c * 8 + 0] * rstd * g0.x + b0.x; y[1] = v[j][c * 8 + 1] * rstd * g0.y + b0.y;
-      y[2] = v[j][c * 8 + 2] * rstd * g0.z + b0.z; y[3] = v[j][c * 8 + 3] * rstd * g0.w + b0.w;
-      y[4] = v[j][c * 8 + 4] * rstd * g1.x + b1v.x; y[5] = v[j][c * 8 + 5] * rstd * g1.y + b1v.y;
-      y[6] = v[j][c * 8 + 6] * rstd * g1.z + b1v.z; y[7] = v[j][c * 8 + 7] * rstd * g1.w + b1v.w;
-      const int k8 = hsel * 8 + j * 4 + c;
-      *reinterpret_cast<uint4*>(dst + k8 * 2048 + r * 16) = pack8_bf16(y);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cb + k0 + 4 * h);
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + k0 + 4 * h);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + k0 + 4 * h);
+        y[4 * h + 0] = (v[c * 8 + 4 * h + 0] + c4.x - mean) * rstd * g4.x + b4.x;
+        y[4 * h + 1] = (v[c * 8 + 4 * h + 1] + c4.y - mean) * rstd * g4.y + b4.y;
+        y[4 * h + 2] = (v[c * 8 + 4 * h + 2] + c4.z - mean) * rstd * g4.z + b4.z;
+        y[4 * h + 3] = (v[c * 8 + 4 * h + 3] + c4.w - mean) * rstd * g4.w + b4.w;
+      }
+      *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
     }
+  }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
@@ -124,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -143,20 +169,18 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ring_load(p.wts, kSlot);
-        ring_load(p.wts + kSlot, kSlot);
+        for (int c = 0; c < 4; ++c) ring_load(p.wts + (size_t)c * kSlot, kSlot);
         for (int blk = 0; blk < p.depth; ++blk) {
           const unsigned char* wb = p.wts + kPatchBytes + (size_t)blk * kBlockBytes;
           mbar_wait(&bars[B_EMPTYP + ps], pphase ^ 1);
           mbar_arrive_expect_tx(&bars[B_FULLP + ps], kParamBytes);
           bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
           if (++ps == 2) { ps = 0; pphase ^= 1; }
-          ring_load(wb + kParamBytes, kQkvBytes);
-          // consumption order: fc1[0] fc1[1] fc2[0] fc1[2] fc2[1] fc2[2]   (blob order: W1_0..2, W2_0..2)
-          const unsigned char* w1 = wb + kParamBytes + kQkvBytes;
-          const unsigned char* w2 = w1 + 3 * (size_t)kSlot;
-          ring_load(w1, kSlot); ring_load(w1 + kSlot, kSlot); ring_load(w2, kSlot);
-          ring_load(w1 + 2 * (size_t)kSlot, kSlot); ring_load(w2 + kSlot, kSlot); ring_load(w2 + 2 * (size_t)kSlot, kSlot);
+          wb += kParamBytes;
+          ring_load(wb, kQkvHalfBytes); wb += kQkvHalfBytes;
+          ring_load(wb, kQkvHalfBytes); wb += kQkvHalfBytes;
+          ring_load(wb, kProjBytes); wb += kProjBytes;
+          for (int c = 0; c < 12; ++c) ring_load(wb + (size_t)c * kSlot, kSlot);   // already in consumption order
         }
       }
     }
@@ -165,13 +189,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
     const int q = warp & 3, hsel = warp >> 2;
     const int r = q * 32 + lane;                                   // row == TMEM lane
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
-    const uint32_t tacc = tx + 128;                                // accumulator columns 128..511
-    const uint32_t sA = smem_u32(smem + OFF_A), sU = smem_u32(smem + OFF_U), sRing = smem_u32(smem + OFF_RING);
-    constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96);
+    const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
+    const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
+    constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
 
-    uint32_t cslot = 0, cphase = 0;       // ring consumer state (meaningful in thread 0)
+    uint32_t cslot = 0, cphase = 0;       // ring consumer cursor (meaningful in thread 0)
     uint32_t ps = 0, pphase = 0;          // param slot
-    uint32_t ph_acc = 0, ph_x = 0, ph_fc1[3] = {0, 0, 0}, ph_h[2] = {0, 0};
+    uint32_t ph_acc = 0, ph_x = 0, ph_fc1[2] = {0, 0}, ph_h[2] = {0, 0};
 
     // issue `ksteps` MMAs consuming the ring slot at the consumer cursor (thread 0 only)
     auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, int ksteps, bool accum_first) {
@@ -193,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
       const int g_cnt = min(p.G, p.RR - rr0);
       const int rows_valid = g_cnt * tokens;
 
-      // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A[128 x 256] ----------------
+      // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A[128 x 256] over A|H ----------------
       for (int i = tid; i < (128 - rows_valid) * 32; i += kCompute) {      // zero the padding rows
         const int rz = rows_valid + i / 32, k8 = i % 32;
         *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
@@ -242,10 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
       bar_compute();
       if (tid == 0) {
         tc_fence_after();
-        mma_from_ring(tmem, sA, ID128, 2048, 8, false);
-        mma_from_ring(tmem, sA + 32768, ID128, 2048, 8, true);
+        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, 4, c > 0);
         umma_commit(&bars[B_ACC]);
       }
+      __syncwarp();
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
       {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383), written back to TMEM once
@@ -258,8 +282,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
           tmem_ld_wait();
           if (r < rows_valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              v[i] = (v[i] + __ldg(p.patch_b + c0 + i)) + __ldg(p.time_pos + tau * 128 + c0 + i) + __ldg(p.freq_pos + f * 128 + c0 + i);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 pb = __ldg(reinterpret_cast<const float4*>(p.patch_b + c0 + i));
+              const float4 tp = __ldg(reinterpret_cast<const float4*>(p.time_pos + tau * 128 + c0 + i));
+              const float4 fp = __ldg(reinterpret_cast<const float4*>(p.freq_pos + f * 128 + c0 + i));
+              v[i] = (v[i] + pb.x) + tp.x + fp.x; v[i + 1] = (v[i + 1] + pb.y) + tp.y + fp.y;
+              v[i + 2] = (v[i + 2] + pb.z) + tp.z + fp.z; v[i + 3] = (v[i + 3] + pb.w) + tp.w + fp.w;
+            }
           }
           tmem_st32(tx + c0, v);
         }
@@ -272,33 +301,35 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         const float* prm = reinterpret_cast<const float*>(smem + OFF_PARAM + ps * kParamBytes);
         const float *ln1_w = prm, *ln1_b = prm + 128, *cb1 = prm + 256, *qkv_b = prm + 384;
         const float *ln2_w = prm + 512, *ln2_b = prm + 640, *cb2 = prm + 768, *b1 = prm + 896;
-        const uint32_t sWproj = smem_u32(smem + OFF_PARAM + ps * kParamBytes + kParamFloats * 4);
 
-        // LN1 -> A ; qkv = A Wqkv^T
+        // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
         ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);
         fence_proxy_async_smem();
         tc_fence_before();
         bar_compute();
         if (tid == 0) {
           tc_fence_after();
-          mma_from_ring(tmem + 128, sA, ID96, 1536, 8, false);
+          mma_from_ring(tmem + 128, sA, ID96, 1536, 4, false);
+          mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, 4, true);
           umma_commit(&bars[B_ACC]);
         }
+        __syncwarp();
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
-        {   // qkv (+bias) -> fp32 scratch [128][97]
-          float* qkv = reinterpret_cast<float*>(smem + OFF_QKV);
-          float v[32], w[16];
-          tmem_ld32(tacc + hsel * 48, v);
-          tmem_ld16(tacc + hsel * 48 + 32, w);
-          tmem_ld_wait();
-          float* dstq = qkv + r * QKV_LD + hsel * 48;
+        {   // qkv (+bias) -> fp32 scratch [128][100]
+          float* dstq = reinterpret_cast<float*>(smem + OFF_QKV) + r * QKV_LD + hsel * 48;
           const float* bq = qkv_b + hsel * 48;
+          float v[32];
+          tmem_ld32(tacc + hsel * 48, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
             *reinterpret_cast<float4*>(dstq + i) = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
           }
+          float w[16];
+          tmem_ld16(tacc + hsel * 48 + 32, w);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bq + 32 + i);
@@ -367,14 +398,14 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         bar_compute();
         if (tid == 0) {   // x += o Wproj^T   (bias deferred into cb2)
           tc_fence_after();
-          umma_bf16(tmem, make_smem_desc(sU, 2048, 128), make_smem_desc(sWproj, 2048, 128), ID128, 1u);
-          umma_bf16(tmem, make_smem_desc(sU + 4096, 2048, 128), make_smem_desc(sWproj + 4096, 2048, 128), ID128, 1u);
+          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, 2, true);
           umma_commit(&bars[B_X]);
         }
+        __syncwarp();
         mbar_wait_all(&bars[B_X], ph_x); ph_x ^= 1;
         tc_fence_after();
 
-        // LN2 -> A ; hidden = relu(A W1^T + b1) ; x += hidden W2^T
+        // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
         ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part, smem + OFF_A);
         fence_proxy_async_smem();
         tc_fence_before();
@@ -382,31 +413,32 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
         if (tid == 0) {
           tc_fence_after();
           for (int c = 0; c < 2; ++c) {
-            mma_from_ring(tmem + 128 + c * 128, sA, ID128, 2048, 8, false);
+            mma_from_ring(tmem + 128 + c * 64, sA, ID64, 1024, 8, false);
             umma_commit(&bars[B_FC1 + c]);
           }
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          mbar_wait_all(&bars[B_FC1 + c], ph_fc1[c]); ph_fc1[c] ^= 1;
-          if (c == 2) { mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1; }   // fc2[0] has finished reading H0
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          const int bsel = c & 1;
+          mbar_wait_all(&bars[B_FC1 + bsel], ph_fc1[bsel]); ph_fc1[bsel] ^= 1;
+          if (c >= 2) { mbar_wait_all(&bars[B_H + bsel], ph_h[bsel]); ph_h[bsel] ^= 1; }   // fc2[c-2] finished reading H[bsel]
           tc_fence_after();
-          unsigned char* H = smem + OFF_U + (c & 1) * 32768;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          unsigned char* H = smem + OFF_H + bsel * 16384;
+          {
             float v[32];
-            tmem_ld32(tacc + c * 128 + hsel * 64 + j * 32, v);
+            tmem_ld32(tacc + bsel * 64 + hsel * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               float y[8];
-              const float* bb = b1 + c * 128 + hsel * 64 + j * 32 + cc * 8;
+              const float* bb = b1 + c * 64 + hsel * 32 + cc * 8;
               const float4 ba = *reinterpret_cast<const float4*>(bb), bc = *reinterpret_cast<const float4*>(bb + 4);
               y[0] = fmaxf(v[cc * 8 + 0] + ba.x, 0.f); y[1] = fmaxf(v[cc * 8 + 1] + ba.y, 0.f);
               y[2] = fmaxf(v[cc * 8 + 2] + ba.z, 0.f); y[3] = fmaxf(v[cc * 8 + 3] + ba.w, 0.f);
               y[4] = fmaxf(v[cc * 8 + 4] + bc.x, 0.f); y[5] = fmaxf(v[cc * 8 + 5] + bc.y, 0.f);
               y[6] = fmaxf(v[cc * 8 + 6] + bc.z, 0.f); y[7] = fmaxf(v[cc * 8 + 7] + bc.w, 0.f);
-              *reinterpret_cast<uint4*>(H + (hsel * 8 + j * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
+              *reinterpret_cast<uint4*>(H + (hsel * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
             }
           }
           fence_proxy_async_smem();
@@ -414,74 +446,62 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
           bar_compute();
           if (tid == 0) {
             tc_fence_after();
-            mma_from_ring(tmem, sU + (c & 1) * 32768, ID128, 2048, 8, true);
-            umma_commit(&bars[B_H + (c & 1)]);
-            if (c == 0) {   // fc1[2] goes behind fc2[0] so that its weights had a ring slot to land in
-              mma_from_ring(tmem + 128 + 2 * 128, sA, ID128, 2048, 8, false);
-              umma_commit(&bars[B_FC1 + 2]);
+            mma_from_ring(tmem, sH + bsel * 16384, ID128, 2048, 4, true);          // fc2[c]: x += H_c W2_c^T
+            umma_commit(&bars[B_H + bsel]);
+            if (c + 2 < 6) {                                                        // fc1[c+2] into the accumulator just drained
+              mma_from_ring(tmem + 128 + bsel * 64, sA, ID64, 1024, 8, false);
+              umma_commit(&bars[B_FC1 + bsel]);
             }
           }
+          __syncwarp();
         }
-        // block end: fc2[1] (H1) and fc2[2] (H0) complete => x is final for this block, params/H buffers reusable
-        mbar_wait_all(&bars[B_H + 1], ph_h[1]); ph_h[1] ^= 1;
+        // block end: fc2[4] (H0) and fc2[5] (H1) complete => x is final for this block, params/H/A reusable
         mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1;
+        mbar_wait_all(&bars[B_H + 1], ph_h[1]); ph_h[1] ^= 1;
         tc_fence_after();
         if (tid == 0) mbar_arrive(&bars[B_EMPTYP + ps]);
+        __syncwarp();
         if (++ps == 2) { ps = 0; pphase ^= 1; }
       }
 
       // ---------------- final LayerNorm (eps 1e-6) + token mean -> pooled[rr][128] ----------------
       {
-        float* Y = reinterpret_cast<float*>(smem + OFF_A);      // [128][132] fp32 over A + U (both idle now)
-        float v[2][32];
-        tmem_ld32(tx + hsel * 64, v[0]);
-        tmem_ld32(tx + hsel * 64 + 32, v[1]);
-        tmem_ld_wait();
-        float s = 0.f;
+        float* Y = reinterpret_cast<float*>(smem + OFF_A);      // [128][128] fp32 over A|H, 16-B chunks XOR-swizzled by row
+        float mean, rstd;
+        row_stats(tx, hsel, r, p.cb_final, 1e-6f, part, mean, rstd);
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v[j][i] += __ldg(p.cb_final + hsel * 64 + j * 32 + i); s += v[j][i]; }
-        if (p.dbg_x != nullptr && r < rows_valid) {
-          float* dx = p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + hsel * 64;
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dx[j * 32 + i] = v[j][i];
-        }
-        part[hsel * 128 + r] = s;
-        bar_compute();
-        const float mean = (part[r] + part[128 + r]) * (1.f / 128.f);
-        float qq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v[j][i] -= mean; qq = fmaf(v[j][i], v[j][i], qq); }
-        part[256 + hsel * 128 + r] = qq;
-        bar_compute();
-        const float rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + 1e-6f);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j) {
+          float v[32];
+          tmem_ld32(tx + hsel * 64 + j * 32, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const int k = hsel * 64 + j * 32 + i;
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cb_final + k));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.norm_b + k));
+            const float x0 = v[i] + c4.x, x1 = v[i + 1] + c4.y, x2 = v[i + 2] + c4.z, x3 = v[i + 3] + c4.w;
+            if (p.dbg_x != nullptr && r < rows_valid)
+              *reinterpret_cast<float4*>(p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + k) = make_float4(x0, x1, x2, x3);
             float4 o;
-            o.x = v[j][i + 0] * rstd * __ldg(p.norm_w + k + 0) + __ldg(p.norm_b + k + 0);
-            o.y = v[j][i + 1] * rstd * __ldg(p.norm_w + k + 1) + __ldg(p.norm_b + k + 1);
-            o.z = v[j][i + 2] * rstd * __ldg(p.norm_w + k + 2) + __ldg(p.norm_b + k + 2);
-            o.w = v[j][i + 3] * rstd * __ldg(p.norm_w + k + 3) + __ldg(p.norm_b + k + 3);
-            *reinterpret_cast<float4*>(&Y[r * Y_LD + k]) = o;
+            o.x = (x0 - mean) * rstd * g4.x + b4.x; o.y = (x1 - mean) * rstd * g4.y + b4.y;
+            o.z = (x2 - mean) * rstd * g4.z + b4.z; o.w = (x3 - mean) * rstd * g4.w + b4.w;
+            *reinterpret_cast<float4*>(&Y[r * 128 + ((((k >> 2) ^ (r & 7)) << 2))]) = o;
           }
+        }
         tc_fence_before();
         bar_compute();
         const int col = tid & 127;
         const float invn = 1.f / (float)tokens;
         for (int g = tid >> 7; g < g_cnt; g += 2) {
           float acc = 0.f;
-          for (int t = 0; t < tokens; ++t) acc += Y[(g * tokens + t) * Y_LD + col];
+          for (int t = 0; t < tokens; ++t) {
+            const int row = g * tokens + t;
+            acc += Y[row * 128 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3))];
+          }
           p.pooled[(size_t)(rr0 + g) * 128 + col] = acc * invn;
         }
-        bar_compute();     // Y (aliases A/U) is free again before the next tile's gather
+        bar_compute();     // Y (aliases A|H) is free again before the next tile's gather
       }
     }
   }
@@ -490,82 +510,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tc_kernel(const TcParams 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, kTmemCols);
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// UMMA plumbing self-test: C[128 x N] (+)= A[128 x K] * Bp^T, Bp already packed (bf16, K-major core-matrix layout).
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bp,
-                                                               const float* __restrict__ Cinit, float* __restrict__ C, int N, int K) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sAp = smem;                   // up to 128 x 256 bf16 = 64 KB
-  unsigned char* sBp = smem + 65536;           // up to 128 x 256 bf16 = 64 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 131072 + 64);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hsel = warp >> 2, r = q * 32 + lane;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)N * K * 2;
-    mbar_arrive_expect_tx(&bars[0], bytes);
-    bulk_g2s(sBp, Bp, bytes, &bars[0]);
-  }
-  // A: thread (r, hsel) converts its half of the k-groups
-  const int k8n = K / 8;
-  for (int k8 = hsel; k8 < k8n; k8 += 2) {
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = A[(size_t)r * K + k8 * 8 + i];
-    *reinterpret_cast<uint4*>(sAp + k8 * 2048 + r * 16) = pack8_bf16(y);
-  }
-  if (Cinit != nullptr) {
-    for (int c0 = hsel * 32; c0 < N; c0 += 64) {
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (c0 + i < N) ? Cinit[(size_t)r * N + c0 + i] : 0.f;
-      tmem_st32(tx + c0, v);
-    }
-    tmem_st_wait();
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) {
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, N);
-    const uint32_t lbo_b = (uint32_t)N * 16;
-    for (int ks = 0; ks < K / 16; ++ks)
-      umma_bf16(tmem, make_smem_desc(smem_u32(sAp) + ks * 4096, 2048, 128), make_smem_desc(smem_u32(sBp) + ks * 2 * lbo_b, lbo_b, 128),
-                idesc, (Cinit != nullptr || ks > 0) ? 1u : 0u);
-    umma_commit(&bars[1]);
-  }
-  mbar_wait(&bars[1], 0);
-  __syncwarp();
-  tc_fence_after();
-  for (int c0 = hsel * 32; c0 < N; c0 += 64) {
-    float v[32];
-    tmem_ld32(tx + c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (c0 + i < N) C[(size_t)r * N + c0 + i] = v[i];
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -573,7 +519,6 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 size_t encoder_tc_bf16_section_bytes(int depth) { return (size_t)kPatchBytes + (size_t)depth * kBlockBytes; }
-size_t encoder_tc_param_bytes() { return kParamBytes; }
 size_t encoder_tc_block_bytes() { return kBlockBytes; }
 
 size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows) {
@@ -617,21 +562,12 @@ int run_encoder_tc(const EncoderArgs& a) {
   UITK_CHECK_CUDA(cudaGetDevice(&dev));
   UITK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const int resident = 2 * sms;                 // two CTAs per SM
+  const int grid = p.num_tiles < resident ? p.num_tiles : resident;
   encoder_tc_kernel<<<grid, kThreads, kSmemBytes, a.stream>>>(p);
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return launch_head_pooled(pooled, a.B, crops, W, lay, cfg.outputdim, a.eval_avg, a.probs, a.stream);
-}
-
-int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float* C, int N, int K, cudaStream_t s) {
-  UITK_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, UITK_EINVAL, "selftest: bad N/K");
-  const int smem = 131072 + 256;
-  UITK_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  umma_selftest_kernel<<<1, 256, smem, s>>>(A, reinterpret_cast<const unsigned char*>(Bp), Cinit, C, N, K);
-  count_launches(1);
-  UITK_CHECK_CUDA(cudaGetLastError());
-  return UITK_OK;
 }
 
 }  // namespace uitk

@@ -214,13 +214,13 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
   unsigned char* sec = reinterpret_cast<unsigned char*>(h_blob) + sizeof(BlobHeader) + fp32_section_bytes(l);
   if (cfg->precision == UITK_PREC_BF16) {
     hdr->bf16_offset = sizeof(BlobHeader) + fp32_section_bytes(l);
-    pack_kmajor(reinterpret_cast<uint16_t*>(sec), t[4], 256, 0, 128, 0, 128);              // patch, k 0..127
-    pack_kmajor(reinterpret_cast<uint16_t*>(sec + 32768), t[4], 256, 0, 128, 128, 128);    // patch, k 128..255
+    for (int c = 0; c < 4; ++c)                                                          // patch weight, K quarters
+      pack_kmajor(reinterpret_cast<uint16_t*>(sec + (size_t)c * 16384), t[4], 256, 0, 128, c * 64, 64);
   }
   for (int i = 0; i < cfg->depth; ++i) {
     const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
     if (cfg->precision == UITK_PREC_BF16) {
-      unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();
+      unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();   // after the 4 x 16 KB patch chunks
       float* prm = reinterpret_cast<float*>(blk);
       memcpy(prm + 0, b[0], 128 * 4); memcpy(prm + 128, b[1], 128 * 4);        // ln1 w, b
       memcpy(prm + 256, cb.data(), 128 * 4);                                   // cb1
@@ -228,13 +228,14 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
       memcpy(prm + 512, b[6], 128 * 4); memcpy(prm + 640, b[7], 128 * 4);      // ln2 w, b
       for (int c = 0; c < 128; ++c) prm[768 + c] = cb[c] + b[5][c];            // cb2 = cb1 + proj bias
       memcpy(prm + 896, b[9], 384 * 4);                                        // fc1 bias
+      // weight chunks in the order the kernel consumes them (csrc/encoder_tc.cu)
       uint16_t* w = reinterpret_cast<uint16_t*>(blk + 1280 * 4);
-      pack_kmajor(w, b[4], 32, 0, 128, 0, 32);                                 // Wproj [128][32]
-      w = reinterpret_cast<uint16_t*>(blk + encoder_tc_param_bytes());
-      pack_kmajor(w, b[2], 128, 0, 96, 0, 128);                                // Wqkv [96][128]
-      w += 96 * 128;
-      for (int c = 0; c < 3; ++c) { pack_kmajor(w, b[8], 128, c * 128, 128, 0, 128); w += 128 * 128; }    // W1 rows c*128..
-      for (int c = 0; c < 3; ++c) { pack_kmajor(w, b[10], 384, 0, 128, c * 128, 128); w += 128 * 128; }   // W2 k-slice c
+      pack_kmajor(w, b[2], 128, 0, 96, 0, 64); w += 96 * 64;                    // Wqkv [96][128], K half 0
+      pack_kmajor(w, b[2], 128, 0, 96, 64, 64); w += 96 * 64;                   // Wqkv, K half 1
+      pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // Wproj [128][32]
+      auto w1 = [&](int c) { pack_kmajor(w, b[8], 128, c * 64, 64, 0, 128); w += 64 * 128; };    // fc1 rows 64c..
+      auto w2 = [&](int c) { pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64; };   // fc2 K slice 64c..
+      w1(0); w1(1); w2(0); w1(2); w2(1); w1(3); w2(2); w1(4); w2(3); w1(5); w2(4); w2(5);
     }
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
   }

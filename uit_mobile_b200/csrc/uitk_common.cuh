@@ -114,7 +114,6 @@ int run_encoder_fp32(const EncoderArgs& a);
 int run_encoder_tc(const EncoderArgs& a);
 int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float* C, int N, int K, cudaStream_t s);
 size_t encoder_tc_bf16_section_bytes(int depth);
-size_t encoder_tc_param_bytes();
 size_t encoder_tc_block_bytes();
 size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows);
 size_t encoder_fp32_workspace_bytes(int64_t rows);   // rows = B * crops * tokens
