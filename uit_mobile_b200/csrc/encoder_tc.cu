@@ -26,7 +26,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 288;          // 8 compute warps + 1 producer warp
+constexpr int kThreads = 320;          // 8 compute warps + TMA producer warp + MMA issuer warp
 constexpr int kCompute = 256;
 constexpr uint32_t kSlot = 16384;
 constexpr int kSlots = 2;
@@ -50,7 +50,7 @@ constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = 2, B_FULLP = 4, B_EMPTYP = 6, B_ACC = 8, B_X = 9, B_FC1 = 10, B_H = 12, B_COUNT = 14 };
+enum { B_FULLW = 0, B_EMPTYW = 2, B_FULLP = 4, B_EMPTYP = 6, B_ACC = 8, B_X = 9, B_FC1 = 10, B_H = 12, B_READY = 14, B_COUNT = 16 };
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_READY || i == B_READY + 1) ? kCompute : 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -184,29 +184,75 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         }
       }
     }
+  } else if (warp == 9) {
+    // =================================== MMA issuer =======================================
+    // One thread issues every tcgen05.mma of the CTA.  It waits for (a) the "operand ready" signal of the 256 compute
+    // threads (alternating mbarriers, count 256) and (b) the weight chunk in the ring; the compute warps never block on
+    // weights, only on the completion barriers (ACC / X / FC1 / H) of the MMAs whose results they read.
+    if (lane == 0) {
+      const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
+      constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
+      uint32_t cslot = 0, cphase = 0, sig = 0;
+      auto wait_ready = [&]() {
+        mbar_wait(&bars[B_READY + (sig & 1)], (sig >> 1) & 1);
+        ++sig;
+        tc_fence_after();
+      };
+      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, int ksteps, bool accum_first) {
+        mbar_wait(&bars[B_FULLW + cslot], cphase);
+        tc_fence_after();
+        const uint32_t b_base = sRing + cslot * kSlot;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
+                    (accum_first || ks > 0) ? 1u : 0u);
+        umma_commit(&bars[B_EMPTYW + cslot]);
+        if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        wait_ready();                                                         // patch operand gathered
+        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, 4, c > 0);
+        umma_commit(&bars[B_ACC]);
+        for (int blk = 0; blk < p.depth; ++blk) {
+          wait_ready();                                                       // LN1 output in A
+          mma_from_ring(tmem + 128, sA, ID96, 1536, 4, false);
+          mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, 4, true);
+          umma_commit(&bars[B_ACC]);
+          wait_ready();                                                       // attention output in A_o
+          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, 2, true);         // x += o Wproj^T (bias deferred into cb2)
+          umma_commit(&bars[B_X]);
+          wait_ready();                                                       // LN2 output in A
+          for (int c = 0; c < 2; ++c) {
+            mma_from_ring(tmem + 128 + c * 64, sA, ID64, 1024, 8, false);
+            umma_commit(&bars[B_FC1 + c]);
+          }
+          for (int c = 0; c < 6; ++c) {
+            const int bsel = c & 1;
+            wait_ready();                                                     // H[bsel] written, accumulator bsel drained
+            mma_from_ring(tmem, sH + bsel * 16384, ID128, 2048, 4, true);     // fc2[c]: x += H_c W2_c^T
+            umma_commit(&bars[B_H + bsel]);
+            if (c + 2 < 6) {                                                  // fc1[c+2] into the accumulator just drained
+              mma_from_ring(tmem + 128 + bsel * 64, sA, ID64, 1024, 8, false);
+              umma_commit(&bars[B_FC1 + bsel]);
+            }
+          }
+        }
+      }
+    }
   } else {
     // =================================== compute warps =======================================
     const int q = warp & 3, hsel = warp >> 2;
     const int r = q * 32 + lane;                                   // row == TMEM lane
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
     const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
-    const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
-    constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
-
-    uint32_t cslot = 0, cphase = 0;       // ring consumer cursor (meaningful in thread 0)
     uint32_t ps = 0, pphase = 0;          // param slot
     uint32_t ph_acc = 0, ph_x = 0, ph_fc1[2] = {0, 0}, ph_h[2] = {0, 0};
-
-    // issue `ksteps` MMAs consuming the ring slot at the consumer cursor (thread 0 only)
-    auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, int ksteps, bool accum_first) {
-      mbar_wait(&bars[B_FULLW + cslot], cphase);
-      tc_fence_after();
-      const uint32_t b_base = sRing + cslot * kSlot;
-      for (int ks = 0; ks < ksteps; ++ks)
-        umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
-                  (accum_first || ks > 0) ? 1u : 0u);
-      umma_commit(&bars[B_EMPTYW + cslot]);
-      if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
+    uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
+    // operand written by this thread is visible to the async proxy, its TMEM reads are done: tell the MMA issuer
+    auto signal_ready = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars[B_READY + (sig & 1)]);
+      ++sig;
     };
 
     const float cutoff = 10.f * log10f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
@@ -261,15 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           }
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      bar_compute();
-      if (tid == 0) {
-        tc_fence_after();
-        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, 4, c > 0);
-        umma_commit(&bars[B_ACC]);
-      }
-      __syncwarp();
+      signal_ready();
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
       {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383), written back to TMEM once
@@ -304,16 +342,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 
         // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
         ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        bar_compute();
-        if (tid == 0) {
-          tc_fence_after();
-          mma_from_ring(tmem + 128, sA, ID96, 1536, 4, false);
-          mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, 4, true);
-          umma_commit(&bars[B_ACC]);
-        }
-        __syncwarp();
+        signal_ready();
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
         {   // qkv (+bias) -> fp32 scratch [128][100]
@@ -394,30 +423,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 0) * 2048 + ar * 16) = pack8_bf16(out);
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 1) * 2048 + ar * 16) = pack8_bf16(out + 8);
         }
-        fence_proxy_async_smem();
-        bar_compute();
-        if (tid == 0) {   // x += o Wproj^T   (bias deferred into cb2)
-          tc_fence_after();
-          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, 2, true);
-          umma_commit(&bars[B_X]);
-        }
-        __syncwarp();
+        signal_ready();
         mbar_wait_all(&bars[B_X], ph_x); ph_x ^= 1;
         tc_fence_after();
 
         // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
         ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part, smem + OFF_A);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        bar_compute();
-        if (tid == 0) {
-          tc_fence_after();
-          for (int c = 0; c < 2; ++c) {
-            mma_from_ring(tmem + 128 + c * 64, sA, ID64, 1024, 8, false);
-            umma_commit(&bars[B_FC1 + c]);
-          }
-        }
-        __syncwarp();
+        signal_ready();
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {
           const int bsel = c & 1;
@@ -441,19 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
               *reinterpret_cast<uint4*>(H + (hsel * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
             }
           }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          bar_compute();
-          if (tid == 0) {
-            tc_fence_after();
-            mma_from_ring(tmem, sH + bsel * 16384, ID128, 2048, 4, true);          // fc2[c]: x += H_c W2_c^T
-            umma_commit(&bars[B_H + bsel]);
-            if (c + 2 < 6) {                                                        // fc1[c+2] into the accumulator just drained
-              mma_from_ring(tmem + 128 + bsel * 64, sA, ID64, 1024, 8, false);
-              umma_commit(&bars[B_FC1 + bsel]);
-            }
-          }
-          __syncwarp();
+          signal_ready();
         }
         // block end: fc2[4] (H0) and fc2[5] (H1) complete => x is final for this block, params/H/A reusable
         mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1;
