@@ -46,7 +46,7 @@ def test_frontend_pack_layout(lib):
     blob = np.zeros(n, np.uint8)
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, n) == 0
     i32, f32 = blob.view(np.int32), blob.view(np.float32)
-    assert i32[0] == 0x55464531 and i32[1] == 500            # SURVEY: 500 non-zeros [probed]
+    assert i32[0] == 0x55464531 and 500 <= i32[1] <= 500 + 3 * 64   # 500 non-zeros [probed] + padding to 4 per mel bin
     np.testing.assert_array_equal(f32[4:516], win.numpy())
     tw256 = f32[516:516 + 512].reshape(256, 2)
     j = np.arange(256)
@@ -55,8 +55,11 @@ def test_frontend_pack_layout(lib):
     lo, cnt, off = i32[base:base + 64], i32[base + 64:base + 128], i32[base + 128:base + 192]
     w = f32[base + 192:]
     dense = np.zeros((257, 64), np.float32)
+    assert (cnt % 4 == 0).all() and (off % 4 == 0).all()
     for m in range(64):
-        dense[lo[m]:lo[m] + cnt[m], m] = w[off[m]:off[m] + cnt[m]]
+        hi = min(257, lo[m] + cnt[m])
+        dense[lo[m]:hi, m] = w[off[m]:off[m] + hi - lo[m]]
+        assert (w[off[m] + hi - lo[m]:off[m] + cnt[m]] == 0).all()
     np.testing.assert_array_equal(dense, fb.numpy())
     # error path: blob too small
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, 16) == -5

@@ -30,7 +30,7 @@ int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const 
   UITK_REQUIRE(d_wav && d_frontend_blob && d_db && d_max_pow, UITK_EINVAL, "null pointer");
   UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
   UITK_REQUIRE(L > UITK_N_FFT / 2, UITK_EINVAL, "reflect padding needs L > 256 samples (got %lld)", (long long)L);
-  UITK_REQUIRE(L < (1ll << 31) * (int64_t)UITK_HOP / 2, UITK_EINVAL, "clip too long");
+  UITK_REQUIRE(L <= (1ll << 30), UITK_EINVAL, "clip too long (max 2^30 samples per row)");
   UITK_REQUIRE(ld_wav >= 1, UITK_EINVAL, "ld_wav must be >= 1");
   UITK_REQUIRE(aligned(d_wav, 4) && aligned(d_db, 4) && aligned(d_max_pow, 4) && aligned(d_frontend_blob, 16), UITK_EALIGN,
                "misaligned pointer");

@@ -268,41 +268,34 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         const int rz = rows_valid + i / 32, k8 = i % 32;
         *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
       }
-      for (int row0 = warp; row0 < g_cnt * 64; row0 += 32) {      // 4 rows (12 loads) in flight per warp
-        float val[4][3];
+      // each warp handles one clip-crop's 64 mel rows at a time (8 rows = 24 coalesced loads in flight per lane)
+      for (int g = 0; g < g_cnt; ++g) {
+        const int rr = rr0 + g;
+        const int b = rr / p.crops, c = rr - b * p.crops;
+        int start = 0;
+        if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
+        const float* src0 = p.db + ((size_t)b * 64 + warp * 8) * p.T + start;     // this warp: mel rows warp*8 .. warp*8+7
+        float val[8][3];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int row = row0 + 8 * u;
-          if (row < g_cnt * 64) {
-            const int g = row >> 6, mel = row & 63;
-            const int rr = rr0 + g;
-            const int b = rr / p.crops, c = rr - b * p.crops;
-            int start = 0;
-            if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
-            const float* src = p.db + ((size_t)b * 64 + mel) * p.T + start;
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int tt = lane + 32 * j;
-              val[u][j] = tt < 16 * t_n ? __ldg(src + tt) : 0.f;
-            }
+          for (int j = 0; j < 3; ++j) {
+            const int tt = lane + 32 * j;
+            val[u][j] = tt < 16 * t_n ? __ldg(src0 + (size_t)u * p.T + tt) : 0.f;
           }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int row = row0 + 8 * u;
-          if (row < g_cnt * 64) {
-            const int g = row >> 6, mel = row & 63;
-            const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
-            const int rbase = g * tokens + (mel >> 4) * t_n;
+        for (int u = 0; u < 8; ++u) {
+          const int mel = warp * 8 + u;
+          const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
+          const int rbase = g * tokens + (mel >> 4) * t_n;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int tt = lane + 32 * j;
-              if (tt < 16 * t_n) {
-                const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
-                const int k = (mel & 15) * 16 + (tt & 15);
-                const int rrow = rbase + (tt >> 4);
-                *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
-              }
+          for (int j = 0; j < 3; ++j) {
+            const int tt = lane + 32 * j;
+            if (tt < 16 * t_n) {
+              const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
+              const int k = (mel & 15) * 16 + (tt & 15);
+              const int rrow = rbase + (tt >> 4);
+              *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
             }
           }
         }

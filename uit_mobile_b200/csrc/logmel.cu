@@ -24,6 +24,16 @@ constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT; 
 constexpr int kExStride = 280;   // float2 per frame group: 16 x 17 used; 560 words = 16 mod 32 so that the two
                                  // frame groups of a warp use complementary banks for 32-bit accesses
 
+// cos / sin (2 pi m / 32), m = 0..15
+__device__ constexpr float kCos32[16] = {1.f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                                         0.55557023301960222f, 0.38268343236508977f, 0.19509032201612827f, 0.f, -0.19509032201612827f,
+                                         -0.38268343236508977f, -0.55557023301960222f, -0.70710678118654752f, -0.83146961230254524f,
+                                         -0.92387953251128674f, -0.98078528040323044f};
+__device__ constexpr float kSin32[16] = {0.f, 0.19509032201612827f, 0.38268343236508977f, 0.55557023301960222f, 0.70710678118654752f,
+                                         0.83146961230254524f, 0.92387953251128674f, 0.98078528040323044f, 1.f, 0.98078528040323044f,
+                                         0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960222f,
+                                         0.38268343236508977f, 0.19509032201612827f};
+
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -66,10 +76,8 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 struct SmemLayout {
   float window[512];
-  float2 tw256[256];
-  float2 tw512[256];
   int mel_lo[64], mel_cnt[64], mel_off[64];
-  float x[kSamplesPerRound];
+  float x[2][kSamplesPerRound];      // double buffered: cp.async stages round r+1 while round r computes
   float2 ex[kFramesPerRound * kExStride];
   float out[64 * 17];
   float red[8];
@@ -90,8 +98,6 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
   const int t_chunk0 = blockIdx.x * kChunk;
 
   for (int i = tid; i < 512; i += kThreads) S.window[i] = blob->window[i];
-  S.tw256[tid] = blob->tw256[tid];
-  S.tw512[tid] = blob->tw512[tid];
   if (tid < 64) {
     S.mel_lo[tid] = blob->mel_lo[tid];
     S.mel_cnt[tid] = blob->mel_cnt[tid];
@@ -103,25 +109,50 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
   const float* clip = wav + b * ld;
   float* out_clip = db + b * 64 * (long long)T;
   float tmax = 0.f;
+  // thread-constant twiddles kept in registers: W256^(j*2^i) (the other powers are products of these) and W512^j
+  const float2 w1 = blob->tw256[1 * 16 + j], w2 = blob->tw256[2 * 16 + j], w4 = blob->tw256[4 * 16 + j], w8 = blob->tw256[8 * 16 + j];
+  const float2 wj512 = blob->tw512[j];
+
+  // Stage the 2912 samples of a round into S.x[buf]: 16-byte cp.async for groups that lie inside the clip (and are
+  // 16-B aligned), synchronous loads with the reflect index map (no edge repeat) for the few groups at the clip edges.
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(clip) & 15) == 0);
+  const int Li = (int)L;
+  auto stage = [&](int round, int buf) {
+    const int t0 = t_chunk0 + round * kFramesPerRound;
+    if (round < kRounds && t0 < T) {
+      const int s0 = t0 * UITK_HOP - UITK_N_FFT / 2;
+      float* dst = S.x[buf];
+      for (int i = tid * 4; i < kSamplesPerRound; i += kThreads * 4) {
+        const int idx = s0 + i;
+        if (vec_ok && idx >= 0 && idx + 3 < Li) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(clip + idx)
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int id = idx + e;
+            if (id < 0) id = -id;
+            if (id >= Li) id = 2 * (Li - 1) - id;
+            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : 0.f;      // frames past T read zeros
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
 
   for (int round = 0; round < kRounds; ++round) {
     const int t0 = t_chunk0 + round * kFramesPerRound;
     if (t0 >= T) break;
-    __syncthreads();   // constants visible; previous round finished with S.x / S.out
-    {
-      const long long s0 = (long long)t0 * UITK_HOP - UITK_N_FFT / 2;
-      for (int i = tid; i < kSamplesPerRound; i += kThreads) {
-        long long idx = s0 + i;
-        if (idx < 0) idx = -idx;                       // reflect (no edge repeat)
-        if (idx >= L) idx = 2 * (L - 1) - idx;
-        S.x[i] = (idx >= 0 && idx < L) ? __ldg(clip + idx) : 0.f;   // frames past T read zeros
-      }
-    }
-    __syncthreads();
+    stage(round + 1, (round + 1) & 1);                 // buffer last read two barriers ago
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();   // S.x[round & 1] (and the constants) visible; previous round's S.out readers are done
+    const float* sx = S.x[round & 1];
 
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
     float2 v[16];
-    const float* xf = S.x + g * UITK_HOP;
+    const float* xf = sx + g * UITK_HOP;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const int n = j + 16 * m;
@@ -130,8 +161,14 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
       v[m] = make_float2(xx.x * ww.x, xx.y * ww.y);
     }
     fft16(v);                                   // over m -> k1
-#pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], S.tw256[k1 * 16 + j]);
+    {   // v[k1] *= W256^(j*k1), powers composed from w1, w2, w4, w8 (<= 3 roundings)
+      const float2 w3 = cmul(w2, w1), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+      v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+      v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
+      v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+      v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
+      v[15] = cmul(v[15], cmul(w8, w7));
+    }
     float2* e = S.ex + g * kExStride;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + j] = v[k1];
@@ -140,20 +177,21 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
     for (int n1 = 0; n1 < 16; ++n1) v[n1] = e[j * 17 + n1];   // this thread now owns k1 = j
     __syncwarp();
     fft16(v);                                   // over n1 -> k2 ; v[k2] = Z[j + 16 k2]
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) e[j + 16 * k2] = v[k2];
-    __syncwarp();
 
-    // ---- real-FFT unpack + power: X[k] = E[k] + W512^k O[k]
+    // ---- real-FFT unpack + power: X[k] = E[k] + W512^k O[k], k = j + 16 m.  The partner Z[256-k] lives in lane
+    // (16-j) of this frame group at register 15-m (lane 0: its own register (16-m)&15): one shuffle, static indices.
+    // W512^k = W512^j * W32^m with W32^m compile-time constants.
     float p[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      const int k = j + 16 * m;
       const float2 zk = v[m];
-      const float2 zn = e[(256 - k) & 255];
+      float2 zn;
+      zn.x = __shfl_sync(0xffffffffu, v[15 - m].x, (16 - j) & 15, 16);
+      zn.y = __shfl_sync(0xffffffffu, v[15 - m].y, (16 - j) & 15, 16);
+      if (j == 0) zn = v[(16 - m) & 15];
       const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
       const float orr = 0.5f * (zk.y + zn.y), oi = -0.5f * (zk.x - zn.x);
-      const float2 w = S.tw512[k];
+      const float2 w = cmul(wj512, make_float2(kCos32[m], -kSin32[m]));
       const float xr = er + (orr * w.x - oi * w.y);
       const float xi = ei + (orr * w.y + oi * w.x);
       p[m] = xr * xr + xi * xi;
@@ -174,8 +212,13 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
     for (int q = 0; q < 4; ++q) {
       const int m = j + 16 * q;
       const int lo = S.mel_lo[m], cnt = S.mel_cnt[m], off = S.mel_off[m];
-      float acc = 0.f;
-      for (int i = 0; i < cnt; ++i) acc = fmaf(s_melw[off + i], pf[lo + i], acc);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int i = 0; i < cnt; i += 4) {           // cnt % 4 == 0, off % 4 == 0 (zero-weight padding by the packer)
+        const float4 w4 = *reinterpret_cast<const float4*>(s_melw + off + i);
+        a0 = fmaf(w4.x, pf[lo + i], a0); a1 = fmaf(w4.y, pf[lo + i + 1], a1);
+        a2 = fmaf(w4.z, pf[lo + i + 2], a2); a3 = fmaf(w4.w, pf[lo + i + 3], a3);
+      }
+      const float acc = (a0 + a1) + (a2 + a3);
       if (live) tmax = fmaxf(tmax, acc);
       S.out[m * 17 + g] = 10.f * log10f(fmaxf(acc, 1e-10f));
     }

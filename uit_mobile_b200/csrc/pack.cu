@@ -128,11 +128,13 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
     for (int k = 0; k < UITK_N_FREQS; ++k)
       if (h_fb[(size_t)k * UITK_N_MELS + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
     if (lo < 0) { fb->mel_lo[m] = 0; fb->mel_cnt[m] = 0; fb->mel_off[m] = n; continue; }
-    const int cnt = hi - lo + 1;
+    // ranges are padded with zero weights to a multiple of 4 entries (the kernel consumes 4 per step; the padded
+    // entries multiply finite scratch values beyond bin 256 by 0)
+    const int cnt = (hi - lo + 1 + 3) / 4 * 4;
     UITK_REQUIRE(n + cnt <= kMaxMelWeights, UITK_EINVAL,
                  "mel filterbank too dense for the kernel (%d packed weights max)", kMaxMelWeights);
     fb->mel_lo[m] = lo; fb->mel_cnt[m] = cnt; fb->mel_off[m] = n;
-    for (int k = lo; k <= hi; ++k) fb->mel_w[n++] = h_fb[(size_t)k * UITK_N_MELS + m];
+    for (int k = lo; k < lo + cnt; ++k) fb->mel_w[n++] = (k <= hi) ? h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
   }
   fb->n_weights = n;
   return UITK_OK;
