@@ -46,21 +46,22 @@ def test_frontend_pack_layout(lib):
     blob = np.zeros(n, np.uint8)
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, n) == 0
     i32, f32 = blob.view(np.int32), blob.view(np.float32)
-    assert i32[0] == 0x55464531 and 500 <= i32[1] <= 500 + 3 * 64   # 500 non-zeros [probed] + padding to 4 per mel bin
+    assert i32[0] == 0x55464531
     np.testing.assert_array_equal(f32[4:516], win.numpy())
     tw256 = f32[516:516 + 512].reshape(256, 2)
     j = np.arange(256)
     np.testing.assert_allclose(tw256[:, 0] + 1j * tw256[:, 1], np.exp(-2j * np.pi * ((j >> 4) * (j & 15)) / 256), atol=1e-7)
     base = 516 + 1024
-    lo, cnt, off = i32[base:base + 64], i32[base + 64:base + 128], i32[base + 128:base + 192]
-    w = f32[base + 192:]
-    dense = np.zeros((257, 64), np.float32)
-    assert (cnt % 4 == 0).all() and (off % 4 == 0).all()
+    lo, iters, qoff = i32[base:base + 64], i32[base + 64:base + 68], i32[base + 68:base + 72]
+    w = f32[base + 80:]
+    assert (lo % 4 == 0).all() and i32[1] == 64 * iters.sum()
+    dense = np.zeros((257 + 64, 64), np.float32)
     for m in range(64):
-        hi = min(257, lo[m] + cnt[m])
-        dense[lo[m]:hi, m] = w[off[m]:off[m] + hi - lo[m]]
-        assert (w[off[m] + hi - lo[m]:off[m] + cnt[m]] == 0).all()
-    np.testing.assert_array_equal(dense, fb.numpy())
+        q, j = divmod(m, 16)
+        for i in range(iters[q]):
+            dense[lo[m] + 4 * i: lo[m] + 4 * i + 4, m] = w[qoff[q] + (i * 16 + j) * 4: qoff[q] + (i * 16 + j) * 4 + 4]
+    np.testing.assert_array_equal(dense[:257], fb.numpy())
+    assert (dense[257:] == 0).all()
     # error path: blob too small
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, 16) == -5
     assert b"needs" in lib.uitk_last_error()

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
     }
   }
   float cutoff = 0.f;
-  if (PRO == PRO_PATCH) cutoff = 10.f * log10f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+  if (PRO == PRO_PATCH) cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
 
   float acc[8][TN];
 #pragma unroll

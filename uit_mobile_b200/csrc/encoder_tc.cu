@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       ++sig;
     };
 
-    const float cutoff = 10.f * log10f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+    const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
     const int tokens = p.tokens, t_n = p.t_n;
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {

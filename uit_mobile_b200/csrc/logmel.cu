@@ -76,7 +76,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 struct SmemLayout {
   float window[512];
-  int mel_lo[64], mel_cnt[64], mel_off[64];
+  int mel_lo[64], mel_iters[4], mel_qoff[4];
   float x[2][kSamplesPerRound];      // double buffered: cp.async stages round r+1 while round r computes
   float2 ex[kFramesPerRound * kExStride];
   float out[64 * 17];
@@ -98,11 +98,8 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
   const int t_chunk0 = blockIdx.x * kChunk;
 
   for (int i = tid; i < 512; i += kThreads) S.window[i] = blob->window[i];
-  if (tid < 64) {
-    S.mel_lo[tid] = blob->mel_lo[tid];
-    S.mel_cnt[tid] = blob->mel_cnt[tid];
-    S.mel_off[tid] = blob->mel_off[tid];
-  }
+  if (tid < 64) S.mel_lo[tid] = blob->mel_lo[tid];
+  if (tid < 4) { S.mel_iters[tid] = blob->mel_iters[tid]; S.mel_qoff[tid] = blob->mel_qoff[tid]; }
   const int nw = blob->n_weights;
   for (int i = tid; i < nw; i += kThreads) s_melw[i] = blob->mel_w[i];
 
@@ -211,16 +208,19 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int m = j + 16 * q;
-      const int lo = S.mel_lo[m], cnt = S.mel_cnt[m], off = S.mel_off[m];
+      const int iters = S.mel_iters[q];
+      const float4* wq = reinterpret_cast<const float4*>(s_melw + S.mel_qoff[q]) + j;     // lane-interleaved weights
+      const float4* pq = reinterpret_cast<const float4*>(pf + S.mel_lo[m]);               // 4-aligned range start
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int i = 0; i < cnt; i += 4) {           // cnt % 4 == 0, off % 4 == 0 (zero-weight padding by the packer)
-        const float4 w4 = *reinterpret_cast<const float4*>(s_melw + off + i);
-        a0 = fmaf(w4.x, pf[lo + i], a0); a1 = fmaf(w4.y, pf[lo + i + 1], a1);
-        a2 = fmaf(w4.z, pf[lo + i + 2], a2); a3 = fmaf(w4.w, pf[lo + i + 3], a3);
+      for (int i = 0; i < iters; ++i) {            // uniform trip count per group; short ranges carry zero weights
+        const float4 w4 = wq[i * 16];
+        const float4 p4 = pq[i];
+        a0 = fmaf(w4.x, p4.x, a0); a1 = fmaf(w4.y, p4.y, a1);
+        a2 = fmaf(w4.z, p4.z, a2); a3 = fmaf(w4.w, p4.w, a3);
       }
       const float acc = (a0 + a1) + (a2 + a3);
       if (live) tmax = fmaxf(tmax, acc);
-      S.out[m * 17 + g] = 10.f * log10f(fmaxf(acc, 1e-10f));
+      S.out[m * 17 + g] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));   // 10 log10(x); |err| ~1e-6 dB
     }
     __syncthreads();
     for (int i = tid; i < 64 * kFramesPerRound; i += kThreads) {
@@ -245,7 +245,7 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
 }
 
 __global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint32_t* __restrict__ max_pow, float top_db) {
-  const float cutoff = 10.f * log10f(fmaxf(__uint_as_float(*max_pow), 1e-10f)) - top_db;
+  const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*max_pow), 1e-10f)) - top_db;   // same map as the kernel
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) db[i] = fmaxf(db[i], cutoff);
 }

@@ -122,19 +122,34 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
     fb->tw256[j] = make_float2((float)cos(two_pi * (ln * k1) / 256.0), (float)-sin(two_pi * (ln * k1) / 256.0));
     fb->tw512[j] = make_float2((float)cos(two_pi * j / 512.0), (float)-sin(two_pi * j / 512.0));
   }
-  int n = 0;
+  int lo_[UITK_N_MELS], hi_[UITK_N_MELS];
   for (int m = 0; m < UITK_N_MELS; ++m) {
     int lo = -1, hi = -1;
     for (int k = 0; k < UITK_N_FREQS; ++k)
       if (h_fb[(size_t)k * UITK_N_MELS + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-    if (lo < 0) { fb->mel_lo[m] = 0; fb->mel_cnt[m] = 0; fb->mel_off[m] = n; continue; }
-    // ranges are padded with zero weights to a multiple of 4 entries (the kernel consumes 4 per step; the padded
-    // entries multiply finite scratch values beyond bin 256 by 0)
-    const int cnt = (hi - lo + 1 + 3) / 4 * 4;
-    UITK_REQUIRE(n + cnt <= kMaxMelWeights, UITK_EINVAL,
+    if (lo < 0) { lo = 0; hi = -1; }
+    lo_[m] = lo & ~3;                    // 4-aligned start: the kernel reads the power spectrum as float4
+    hi_[m] = hi;
+    fb->mel_lo[m] = lo_[m];
+  }
+  int n = 0;
+  for (int q = 0; q < 4; ++q) {
+    int iters = 0;
+    for (int j = 0; j < 16; ++j) {
+      const int m = 16 * q + j, len = hi_[m] - lo_[m] + 1;
+      if ((len + 3) / 4 > iters) iters = (len + 3) / 4;
+    }
+    UITK_REQUIRE(n + iters * 64 <= kMaxMelWeights, UITK_EINVAL,
                  "mel filterbank too dense for the kernel (%d packed weights max)", kMaxMelWeights);
-    fb->mel_lo[m] = lo; fb->mel_cnt[m] = cnt; fb->mel_off[m] = n;
-    for (int k = lo; k < lo + cnt; ++k) fb->mel_w[n++] = (k <= hi) ? h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
+    fb->mel_iters[q] = iters;
+    fb->mel_qoff[q] = n;
+    for (int i = 0; i < iters; ++i)
+      for (int j = 0; j < 16; ++j)
+        for (int e = 0; e < 4; ++e) {
+          const int m = 16 * q + j, k = lo_[m] + 4 * i + e;
+          fb->mel_w[n + (i * 16 + j) * 4 + e] = (k <= hi_[m] && k < UITK_N_FREQS) ? h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
+        }
+    n += iters * 64;
   }
   fb->n_weights = n;
   return UITK_OK;

@@ -32,7 +32,7 @@ void count_launches(int n);   // process-wide counter behind uitk_kernel_launche
 // ---------------------------------------------------------------------------------------------------------
 // Front-end constant blob (device layout).  All fields 4 bytes; header first.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kMaxMelWeights = 1024;   // packed (dense-range) filterbank entries kept in shared memory (HTK/64: ~560)
+constexpr int kMaxMelWeights = 2048;   // packed filterbank entries kept in shared memory (HTK/64: 1024 incl. padding)
 
 struct FrontendBlob {
   int magic;                 // 'UFE1'
@@ -41,9 +41,12 @@ struct FrontendBlob {
   float window[512];         // front_end.0.spectrogram.window
   float2 tw256[256];         // [k1*16 + lane] = exp(-2*pi*i*lane*k1/256)
   float2 tw512[256];         // exp(-2*pi*i*k/512)
-  int mel_lo[64];            // first frequency bin with a non-zero weight for mel bin m
-  int mel_cnt[64];           // number of consecutive bins
-  int mel_off[64];           // offset into mel_w
+  int mel_lo[64];            // first frequency bin of mel bin m's range, rounded down to a multiple of 4
+  int mel_iters[4];          // float4 steps for the mel bins {16q .. 16q+15} (max range of the group / 4)
+  int mel_qoff[4];           // float offset of group q's weights in mel_w
+  int pad2[8];
+  // group q, step i, lane j (mel bin 16q+j): 4 weights for bins lo+4i .. lo+4i+3 at mel_w[qoff + (i*16 + j)*4]; the 16
+  // lanes of a frame group read 16 consecutive float4 (conflict-free), shorter ranges are zero padded
   float mel_w[kMaxMelWeights];
 };
 constexpr int kFrontendMagic = 0x55464531;
