@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 100
+#define UITK_VERSION 101
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
@@ -84,9 +84,12 @@ UITK_API int uitk_pack_frontend(const float* h_window, const float* h_fb, void* 
  *              order == float order).  Caller zero-initialises; the kernel atomically maxes into it.
  *              The reference's single batch-global cutoff (Q2) is max_db - 120 with
  *              max_db = 10*log10(max(max_pow, 1e-10)); it is applied by uitk_clamp_db / uitk_encoder, after
- *              the caller has had the chance to all-reduce(max) the word across GPUs. */
+ *              the caller has had the chance to all-reduce(max) the word across GPUs.
+ *   d_min_pow  optional (may be NULL): same for the running MIN mel power; caller initialises to 0x7f800000 (+inf).
+ *              A pipelined caller that encodes chunk i with the running maximum of chunks <= i uses it to prove
+ *              afterwards that the clamp was inactive (min_db >= final max_db - 120) and the result therefore exact. */
 UITK_API int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const void* d_frontend_blob,
-                float* d_db, uint32_t* d_max_pow, void* stream);
+                float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream);
 
 /* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120). */
 UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream);

@@ -67,7 +67,7 @@ def assert_logmel_close(got, x, ref32):
 
 def test_library_loaded_is_in_tree():
     from uit_mobile_b200 import _native as N
-    assert N.lib().uitk_version() == 100
+    assert N.lib().uitk_version() == 101
     assert N.LIB_PATH.endswith("uit_mobile_b200/libuitk.so")
 
 
@@ -192,6 +192,25 @@ def test_batch_chunking_is_invisible():
         assert torch.equal(full, m(x))
     finally:
         m.max_clips_per_launch = old
+
+
+def test_host_pipeline_matches_device_path_and_handles_q2():
+    """HostPipeline (pinned host in/out, chunked, speculative per-chunk encode) == model(x) bit for bit, including the
+    batch where the top-dB clamp is active (silent clip + loud clip => exact re-run with the final maximum)."""
+    from uit_mobile_b200.pipeline import HostPipeline
+    m = model("uit_xxs", "trained", "bf16")
+    pipe = HostPipeline(m, 300, 16000, chunk=64)
+    x = torch.from_numpy(H.noise_clips(300, seed=31))
+    want = m(x.to(DEV)).cpu()
+    got = pipe(x.pin_memory()).clone()
+    assert torch.equal(want, got) and pipe.respeculated == 0
+    adv = torch.from_numpy(np.concatenate([H.noise_clips(70, seed=32, amp=1e-3), H.adversarial_batch()]))   # loud clips LAST
+    want = m(adv.to(DEV)).cpu()
+    got = pipe(adv.pin_memory()).clone()
+    assert pipe.respeculated == 1
+    assert torch.equal(want, got)
+    with pytest.raises(ValueError):
+        pipe(torch.zeros(301, 16000).pin_memory())
 
 
 def test_errors_are_loud():

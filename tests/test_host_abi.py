@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.uitk_version() == 100
+    assert lib.uitk_version() == 101
 
 
 def test_geometry_helpers_match_oracle(lib):
@@ -82,10 +82,10 @@ def test_encoder_pack_tensor_order_and_size(lib):
 
 
 def test_launch_entry_points_validate_before_touching_cuda(lib):
-    assert lib.uitk_logmel(None, 1, 16000, 16000, None, None, None, None) == -1
+    assert lib.uitk_logmel(None, 1, 16000, 16000, None, None, None, None, None) == -1
     one = C.c_float(0)
     p = C.addressof(one)
-    assert lib.uitk_logmel(p, 1, 100, 100, p, p, p, None) == -1 and b"reflect" in lib.uitk_last_error()
+    assert lib.uitk_logmel(p, 1, 100, 100, p, p, p, None, None) == -1 and b"reflect" in lib.uitk_last_error()
 
 
 def test_module_contract():

@@ -26,7 +26,7 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 extern "C" {
 
 int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const void* d_frontend_blob, float* d_db,
-                uint32_t* d_max_pow, void* stream) {
+                uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream) {
   UITK_REQUIRE(d_wav && d_frontend_blob && d_db && d_max_pow, UITK_EINVAL, "null pointer");
   UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
   UITK_REQUIRE(L > UITK_N_FFT / 2, UITK_EINVAL, "reflect padding needs L > 256 samples (got %lld)", (long long)L);
@@ -37,7 +37,7 @@ int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const 
   if (B == 0) return UITK_OK;
   int rc = check_arch();
   if (rc != UITK_OK) return rc;
-  return launch_logmel(d_wav, B, L, ld_wav, reinterpret_cast<const FrontendBlob*>(d_frontend_blob), d_db, d_max_pow,
+  return launch_logmel(d_wav, B, L, ld_wav, reinterpret_cast<const FrontendBlob*>(d_frontend_blob), d_db, d_max_pow, d_min_pow,
                        reinterpret_cast<cudaStream_t>(stream));
 }
 

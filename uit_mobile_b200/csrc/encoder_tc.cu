@@ -44,8 +44,8 @@ constexpr uint32_t OFF_AO = OFF_A;                 // 8 KB attention output oper
 constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 = 51200 B (ends inside H)
 constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
 constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 5120
-constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 4 x 128 floats
-constexpr uint32_t OFF_BAR = OFF_PART + 4 * 128 * 4;
+constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 2 x 512 floats
+constexpr uint32_t OFF_BAR = OFF_PART + 2 * 512 * 4;   // two alternating buffers of [2][128] float2 partial sums
 constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr uint32_t kTmemCols = 256;
@@ -71,11 +71,12 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 }
 
-// Row statistics of (x + cb) for this thread's row; the two threads of a row (hsel 0/1) each reduce 64 columns and
-// exchange partial sums through `part`.  Three cheap passes over TMEM keep the live register count at 32 values.
+// Row statistics of (x + cb) for this thread's row in ONE pass (sum and sum of squares; var = E[x^2] - mean^2 in fp32:
+// |mean| is O(std) for these activations, the cancellation costs < 1e-6 relative).  The two threads of a row
+// (hsel 0/1) each reduce 64 columns and exchange partial sums through `part` with a single barrier.
 __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part, float& mean,
                                           float& rstd) {
-  float s = 0.f;
+  float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float v[32];
@@ -84,35 +85,26 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const fl
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
-      s += ((v[i] + c4.x) + (v[i + 1] + c4.y)) + ((v[i + 2] + c4.z) + (v[i + 3] + c4.w));
+      const float x0 = v[i] + c4.x, x1 = v[i + 1] + c4.y, x2 = v[i + 2] + c4.z, x3 = v[i + 3] + c4.w;
+      s += (x0 + x1) + (x2 + x3);
+      ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
     }
   }
-  part[hsel * 128 + r] = s;
+  *reinterpret_cast<float2*>(part + (hsel * 128 + r) * 2) = make_float2(s, ss);
   bar_compute();
-  mean = (part[r] + part[128 + r]) * (1.f / 128.f);
-  float q = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    float v[32];
-    tmem_ld32(tx + hsel * 64 + j * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
-      const float d0 = v[i] + c4.x - mean, d1 = v[i + 1] + c4.y - mean, d2 = v[i + 2] + c4.z - mean, d3 = v[i + 3] + c4.w - mean;
-      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-    }
-  }
-  part[256 + hsel * 128 + r] = q;
-  bar_compute();
-  rstd = rsqrtf((part[256 + r] + part[384 + r]) * (1.f / 128.f) + eps);
+  const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (128 + r) * 2);
+  mean = (p0.x + p1.x) * (1.f / 128.f);
+  const float var = fmaxf((p0.y + p1.y) * (1.f / 128.f) - mean * mean, 0.f);
+  rstd = rsqrtf(var + eps);
 }
 
 // LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
+// `part` is double buffered by the caller (alternating halves) so that one barrier per LayerNorm suffices.
 __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, const float* gamma,
                                               const float* beta, float eps, float* part, unsigned char* dst) {
   float mean, rstd;
   row_stats(tx, hsel, r, cb, eps, part, mean, rstd);
+  const float nmr = -mean * rstd;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float v[32];
@@ -127,10 +119,10 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
         const float4 c4 = *reinterpret_cast<const float4*>(cb + k0 + 4 * h);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + k0 + 4 * h);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + k0 + 4 * h);
-        y[4 * h + 0] = (v[c * 8 + 4 * h + 0] + c4.x - mean) * rstd * g4.x + b4.x;
-        y[4 * h + 1] = (v[c * 8 + 4 * h + 1] + c4.y - mean) * rstd * g4.y + b4.y;
-        y[4 * h + 2] = (v[c * 8 + 4 * h + 2] + c4.z - mean) * rstd * g4.z + b4.z;
-        y[4 * h + 3] = (v[c * 8 + 4 * h + 3] + c4.w - mean) * rstd * g4.w + b4.w;
+        y[4 * h + 0] = fmaf(fmaf(v[c * 8 + 4 * h + 0] + c4.x, rstd, nmr), g4.x, b4.x);
+        y[4 * h + 1] = fmaf(fmaf(v[c * 8 + 4 * h + 1] + c4.y, rstd, nmr), g4.y, b4.y);
+        y[4 * h + 2] = fmaf(fmaf(v[c * 8 + 4 * h + 2] + c4.z, rstd, nmr), g4.z, b4.z);
+        y[4 * h + 3] = fmaf(fmaf(v[c * 8 + 4 * h + 3] + c4.w, rstd, nmr), g4.w, b4.w);
       }
       *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
     }
@@ -334,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         const float *ln2_w = prm + 512, *ln2_b = prm + 640, *cb2 = prm + 768, *b1 = prm + 896;
 
         // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
-        ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);
+        ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);            // stats buffer 0
         signal_ready();
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
@@ -421,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         tc_fence_after();
 
         // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
-        ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part, smem + OFF_A);
+        ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part + 512, smem + OFF_A);      // stats buffer 1
         signal_ready();
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {

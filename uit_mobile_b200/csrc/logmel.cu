@@ -80,13 +80,14 @@ struct SmemLayout {
   float x[2][kSamplesPerRound];      // double buffered: cp.async stages round r+1 while round r computes
   float2 ex[kFramesPerRound * kExStride];
   float out[64 * 17];
-  float red[8];
+  float red[16];
   // followed by mel_w[n_weights]
 };
 
 __global__ void __launch_bounds__(kThreads, 3)
 logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
-              const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow) {
+              const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
+              uint32_t* __restrict__ min_pow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   float* s_melw = reinterpret_cast<float*>(smem_raw + sizeof(SmemLayout));
@@ -105,7 +106,7 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
 
   const float* clip = wav + b * ld;
   float* out_clip = db + b * 64 * (long long)T;
-  float tmax = 0.f;
+  float tmax = 0.f, tmin = INFINITY;
   // thread-constant twiddles kept in registers: W256^(j*2^i) (the other powers are products of these) and W512^j
   const float2 w1 = blob->tw256[1 * 16 + j], w2 = blob->tw256[2 * 16 + j], w4 = blob->tw256[4 * 16 + j], w8 = blob->tw256[8 * 16 + j];
   const float2 wj512 = blob->tw512[j];
@@ -219,7 +220,7 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
         a2 = fmaf(w4.z, p4.z, a2); a3 = fmaf(w4.w, p4.w, a3);
       }
       const float acc = (a0 + a1) + (a2 + a3);
-      if (live) tmax = fmaxf(tmax, acc);
+      if (live) { tmax = fmaxf(tmax, acc); tmin = fminf(tmin, acc); }
       S.out[m * 17 + g] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));   // 10 log10(x); |err| ~1e-6 dB
     }
     __syncthreads();
@@ -232,15 +233,19 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
 
   // ---- global max of the mel power (non-negative: uint order == float order)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+  }
   __syncthreads();
-  if ((tid & 31) == 0) S.red[tid >> 5] = tmax;
+  if ((tid & 31) == 0) { S.red[tid >> 5] = tmax; S.red[8 + (tid >> 5)] = tmin; }
   __syncthreads();
   if (tid == 0) {
-    float m = S.red[0];
+    float m = S.red[0], mn = S.red[8];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, S.red[w]);
+    for (int w = 1; w < kThreads / 32; ++w) { m = fmaxf(m, S.red[w]); mn = fminf(mn, S.red[8 + w]); }
     atomicMax(max_pow, __float_as_uint(m));
+    if (min_pow != nullptr) atomicMin(min_pow, __float_as_uint(fmaxf(mn, 0.f)));
   }
 }
 
@@ -253,7 +258,7 @@ __global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint3
 }  // namespace
 
 int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
-                  uint32_t* max_pow, cudaStream_t s) {
+                  uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
   const int64_t T = 1 + L / UITK_HOP;
   const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
   UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -262,7 +267,7 @@ int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const Fron
     const int nb = (int)((B - b0) < 65535 ? (B - b0) : 65535);
     dim3 grid(chunks, nb);
     logmel_kernel<<<grid, kThreads, smem, s>>>(wav + b0 * ld, (long long)L, (long long)ld, (int)T, blob,
-                                               db + b0 * 64 * T, max_pow);
+                                               db + b0 * 64 * T, max_pow, min_pow);
     count_launches(1);
   }
   UITK_CHECK_CUDA(cudaGetLastError());

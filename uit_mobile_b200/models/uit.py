@@ -181,7 +181,8 @@ class FrontEnd(nn.Sequential):
         return cache["blob"]
 
     def logmel_unclamped(self, x: torch.Tensor, ld: Optional[int] = None, B: Optional[int] = None, L: Optional[int] = None,
-                         out: Optional[torch.Tensor] = None, max_pow: Optional[torch.Tensor] = None):
+                         out: Optional[torch.Tensor] = None, max_pow: Optional[torch.Tensor] = None,
+                         min_pow: Optional[torch.Tensor] = None):
         """Launch K1.  Returns (dB [B,64,T] un-clamped, max-power word [1] int32).  ``ld/B/L`` describe strided
         views (sliding windows over one long stream) without materialising them.  ``out`` / ``max_pow`` let a
         pipelined caller write chunks of one batch into a shared buffer and keep ONE running maximum (Q2)."""
@@ -206,7 +207,8 @@ class FrontEnd(nn.Sequential):
             max_pow = torch.zeros(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
             N.check(l.uitk_logmel(x.data_ptr(), B, L, ld, self._blob(x.device).data_ptr(), out.data_ptr(),
-                                  max_pow.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "uitk_logmel")
+                                  max_pow.data_ptr(), None if min_pow is None else min_pow.data_ptr(),
+                                  torch.cuda.current_stream(x.device).cuda_stream), "uitk_logmel")
         return out, max_pow
 
 
@@ -328,13 +330,18 @@ class UITBase(nn.Module):
             self._packed = {"key": key, "blob": blob.to(device)}
         return self._packed["blob"]
 
-    def encode(self, db: torch.Tensor, max_pow: torch.Tensor) -> torch.Tensor:
+    def encode(self, db: torch.Tensor, max_pow: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """init_bn + crops + forward_features + forward_head on un-clamped log-mel (uit.py:460-492)."""
         l = N.lib()
         B, _, T = db.shape
         cfg = self._cfg()
         blob = self._encoder_blob(db.device)
-        probs = torch.empty((B, self.outputdim), dtype=torch.float32, device=db.device)
+        if out is None:
+            probs = torch.empty((B, self.outputdim), dtype=torch.float32, device=db.device)
+        else:
+            if tuple(out.shape) != (B, self.outputdim) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float32 [B, outputdim] tensor")
+            probs = out
         step = max(1, self.max_clips_per_launch // int(l.uitk_num_crops(T, self.target_length)))
         stream = torch.cuda.current_stream(db.device).cuda_stream
         with torch.cuda.device(db.device):

@@ -2,35 +2,56 @@
 
 This is what a caller sitting where the reference's DataLoader/`inference.py` sits uses when the audio is in host
 memory (reference: evaluate.py:53-66 moves every batch host->device and reads the scores back).  The batch is cut
-into chunks; the H2D copy of chunk i+1 overlaps the log-mel kernel of chunk i on a second stream.  Because the
-top-dB cutoff is batch-global (Q2) every chunk maxes into ONE device word and the encoder runs after the last
-chunk's front-end; the scores return through one pinned D2H copy.
+into chunks; the H2D copy of chunk i+1 (second stream) overlaps the log-mel AND encoder kernels of chunk i.
+
+The reference's top-dB cutoff is batch-global (Q2: max over the whole batch - 120 dB), which would force the encoder
+to wait for the last chunk's front-end.  Instead every chunk is encoded *speculatively* with the running maximum of
+the chunks seen so far, while the kernels also track the batch-wide MIN mel power.  A running cutoff is never above
+the final one, so if `min_db >= final_max_db - 120` no value of any chunk was (or would have been) clamped and the
+speculative result is exactly the reference's; otherwise (a >120 dB dynamic range inside one batch, e.g. digital
+silence next to a loud clip) the encoder is simply re-run for the whole batch with the final maximum.  Both words
+come back with the scores in the same D2H, so the check costs nothing.
 """
 from __future__ import annotations
 
+import math
+import struct
 from typing import Optional
 
 import torch
 
 from . import _native as N
 
+_INF_BITS = 0x7F800000
+
+
+def _bits_to_db(bits: int) -> float:
+    p = struct.unpack("<f", struct.pack("<I", bits & 0xFFFFFFFF))[0]
+    return 10.0 * math.log10(max(p, 1e-10))
+
 
 class HostPipeline:
-    def __init__(self, model, max_batch: int, L: int = 16000, chunk: int = 1024, device: Optional[torch.device] = None):
+    def __init__(self, model, max_batch: int, L: int = 16000, chunk: int = 1024, device: Optional[torch.device] = None,
+                 speculative: bool = True):
         self.model = model
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise N.UitkError("HostPipeline needs the model on a CUDA device (no CPU fallback)")
         self.max_batch, self.L, self.chunk = max_batch, L, min(chunk, max_batch)
+        self.speculative = speculative
         T = int(N.lib().uitk_num_frames(L))
         dev = self.device
         self.stage = [torch.empty((self.chunk, L), dtype=torch.float32, device=dev) for _ in range(2)]
         self.db = torch.empty((max_batch, 64, T), dtype=torch.float32, device=dev)
-        self.max_pow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.words = torch.zeros(2, dtype=torch.int32, device=dev)          # [max power bits, min power bits]
+        self.probs = torch.empty((max_batch, model.outputdim), dtype=torch.float32, device=dev)
         self.out_host = torch.empty((max_batch, model.outputdim), dtype=torch.float32).pin_memory()
+        self.words_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.words_init = torch.tensor([0, _INF_BITS], dtype=torch.int32, device=dev)
         self.copy_stream = torch.cuda.Stream(dev)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.respeculated = 0          # how many calls needed the exact re-run
 
     @torch.no_grad()
     def __call__(self, wav_host: torch.Tensor) -> torch.Tensor:
@@ -41,10 +62,15 @@ class HostPipeline:
         if B > self.max_batch:
             raise ValueError(f"batch {B} exceeds the pipeline capacity {self.max_batch}")
         m = self.model
+        if m.training:
+            raise NotImplementedError("inference only: call model.eval()")
         main = torch.cuda.current_stream(self.device)
-        self.max_pow.zero_()
+        self.words.copy_(self.words_init)
+        max_w, min_w = self.words[0:1], self.words[1:2]
         self.copy_stream.wait_stream(main)
-        free = [None, None]          # compute-done events per staging buffer
+        sharded = m.process_group is not None
+        spec = self.speculative and not sharded       # sharded: the scope is the global batch -> encode after the all-reduce
+        free = [None, None]                           # compute-done events per staging buffer
         for i, b0 in enumerate(range(0, B, self.chunk)):
             nb = min(self.chunk, B - b0)
             buf = self.stage[i & 1][:nb]
@@ -55,16 +81,29 @@ class HostPipeline:
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
-            m.front_end.logmel_unclamped(buf, out=self.db[b0:b0 + nb], max_pow=self.max_pow)
+            db_i = self.db[b0:b0 + nb]
+            m.front_end.logmel_unclamped(buf, out=db_i, max_pow=max_w, min_pow=min_w)
             done = torch.cuda.Event()
             done.record(main)
             free[i & 1] = done
-        if m.process_group is not None:
-            torch.distributed.all_reduce(self.max_pow, op=torch.distributed.ReduceOp.MAX, group=m.process_group)
-        probs = m.encode(self.db[:B], self.max_pow)
+            if spec:
+                m.encode(db_i, max_w, out=self.probs[b0:b0 + nb])
+        if sharded:
+            torch.distributed.all_reduce(max_w, op=torch.distributed.ReduceOp.MAX, group=m.process_group)
+        if not spec:
+            m.encode(self.db[:B], max_w, out=self.probs[:B])
         out = self.out_host[:B]
-        out.copy_(probs, non_blocking=True)
+        out.copy_(self.probs[:B], non_blocking=True)
+        self.words_host.copy_(self.words, non_blocking=True)
         main.synchronize()
+        if spec:
+            mx, mn = int(self.words_host[0]), int(self.words_host[1])
+            if _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:      # conservative margin vs the device's log2-based dB
+                # some value lies below the final cutoff: redo the encoder with the final batch maximum (exact path)
+                self.respeculated += 1
+                m.encode(self.db[:B], max_w, out=self.probs[:B])
+                out.copy_(self.probs[:B], non_blocking=True)
+                main.synchronize()
         self.h2d_bytes = B * self.L * 4
-        self.d2h_bytes = B * m.outputdim * 4
+        self.d2h_bytes = B * m.outputdim * 4 + 8
         return out
