@@ -76,7 +76,7 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
 // (hsel 0/1) each reduce 64 columns and exchange partial sums through `part` with a single barrier.
 __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part, float& mean,
                                           float& rstd) {
-  float s = 0.f, ss = 0.f;
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);     // packed fp32x2 accumulators (even, odd columns)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float v[32];
@@ -85,11 +85,14 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const fl
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
-      const float x0 = v[i] + c4.x, x1 = v[i + 1] + c4.y, x2 = v[i + 2] + c4.z, x3 = v[i + 3] + c4.w;
-      s += (x0 + x1) + (x2 + x3);
-      ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+      const float2 xa = add2(make_float2(v[i], v[i + 1]), make_float2(c4.x, c4.y));
+      const float2 xb = add2(make_float2(v[i + 2], v[i + 3]), make_float2(c4.z, c4.w));
+      s2 = add2(s2, add2(xa, xb));
+      q2 = fma2(xa, xa, q2);
+      q2 = fma2(xb, xb, q2);
     }
   }
+  const float s = s2.x + s2.y, ss = q2.x + q2.y;
   *reinterpret_cast<float2*>(part + (hsel * 128 + r) * 2) = make_float2(s, ss);
   bar_compute();
   const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (128 + r) * 2);
@@ -104,7 +107,7 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
                                               const float* beta, float eps, float* part, unsigned char* dst) {
   float mean, rstd;
   row_stats(tx, hsel, r, cb, eps, part, mean, rstd);
-  const float nmr = -mean * rstd;
+  const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float v[32];
@@ -119,10 +122,11 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
         const float4 c4 = *reinterpret_cast<const float4*>(cb + k0 + 4 * h);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + k0 + 4 * h);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + k0 + 4 * h);
-        y[4 * h + 0] = fmaf(fmaf(v[c * 8 + 4 * h + 0] + c4.x, rstd, nmr), g4.x, b4.x);
-        y[4 * h + 1] = fmaf(fmaf(v[c * 8 + 4 * h + 1] + c4.y, rstd, nmr), g4.y, b4.y);
-        y[4 * h + 2] = fmaf(fmaf(v[c * 8 + 4 * h + 2] + c4.z, rstd, nmr), g4.z, b4.z);
-        y[4 * h + 3] = fmaf(fmaf(v[c * 8 + 4 * h + 3] + c4.w, rstd, nmr), g4.w, b4.w);
+        const float2 ya = fma2(fma2(add2(make_float2(v[c * 8 + 4 * h], v[c * 8 + 4 * h + 1]), make_float2(c4.x, c4.y)), rs2, nm2),
+                               make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+        const float2 yb = fma2(fma2(add2(make_float2(v[c * 8 + 4 * h + 2], v[c * 8 + 4 * h + 3]), make_float2(c4.z, c4.w)), rs2, nm2),
+                               make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+        y[4 * h + 0] = ya.x; y[4 * h + 1] = ya.y; y[4 * h + 2] = yb.x; y[4 * h + 3] = yb.y;
       }
       *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
     }
@@ -355,9 +359,9 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         {   // attention: thread = (row, head); softmax((q k^T) * 0.125) v   (uit.py:115-119)
           const float* qkv = reinterpret_cast<const float*>(smem + OFF_QKV);
           const int ar = tid & 127, h = tid >> 7;
-          float out[16];
+          float2 o2[8];
 #pragma unroll
-          for (int d = 0; d < 16; ++d) out[d] = 0.f;
+          for (int d = 0; d < 8; ++d) o2[d] = make_float2(0.f, 0.f);
           if (ar < rows_valid) {
             const int base = (ar / tokens) * tokens;
             float qv[16];
@@ -395,16 +399,18 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
               if (j < tokens) {
                 const float pj = sc[j] * inv;
+                const float2 pp = make_float2(pj, pj);
                 const float4* vj = reinterpret_cast<const float4*>(qkv + (base + j) * QKV_LD + 64 + h * 16);
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                   const float4 v4 = vj[d];
-                  out[4 * d] = fmaf(pj, v4.x, out[4 * d]); out[4 * d + 1] = fmaf(pj, v4.y, out[4 * d + 1]);
-                  out[4 * d + 2] = fmaf(pj, v4.z, out[4 * d + 2]); out[4 * d + 3] = fmaf(pj, v4.w, out[4 * d + 3]);
+                  o2[2 * d] = fma2(pp, make_float2(v4.x, v4.y), o2[2 * d]);
+                  o2[2 * d + 1] = fma2(pp, make_float2(v4.z, v4.w), o2[2 * d + 1]);
                 }
               }
             }
           }
+          const float* out = reinterpret_cast<const float*>(o2);
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 0) * 2048 + ar * 16) = pack8_bf16(out);
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 1) * 2048 + ar * 16) = pack8_bf16(out + 8);
         }
@@ -431,10 +437,12 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
               float y[8];
               const float* bb = b1 + c * 64 + hsel * 32 + cc * 8;
               const float4 ba = *reinterpret_cast<const float4*>(bb), bc = *reinterpret_cast<const float4*>(bb + 4);
-              y[0] = fmaxf(v[cc * 8 + 0] + ba.x, 0.f); y[1] = fmaxf(v[cc * 8 + 1] + ba.y, 0.f);
-              y[2] = fmaxf(v[cc * 8 + 2] + ba.z, 0.f); y[3] = fmaxf(v[cc * 8 + 3] + ba.w, 0.f);
-              y[4] = fmaxf(v[cc * 8 + 4] + bc.x, 0.f); y[5] = fmaxf(v[cc * 8 + 5] + bc.y, 0.f);
-              y[6] = fmaxf(v[cc * 8 + 6] + bc.z, 0.f); y[7] = fmaxf(v[cc * 8 + 7] + bc.w, 0.f);
+              const float2 t0 = add2(make_float2(v[cc * 8 + 0], v[cc * 8 + 1]), make_float2(ba.x, ba.y));
+              const float2 t1 = add2(make_float2(v[cc * 8 + 2], v[cc * 8 + 3]), make_float2(ba.z, ba.w));
+              const float2 t2 = add2(make_float2(v[cc * 8 + 4], v[cc * 8 + 5]), make_float2(bc.x, bc.y));
+              const float2 t3 = add2(make_float2(v[cc * 8 + 6], v[cc * 8 + 7]), make_float2(bc.z, bc.w));
+              y[0] = fmaxf(t0.x, 0.f); y[1] = fmaxf(t0.y, 0.f); y[2] = fmaxf(t1.x, 0.f); y[3] = fmaxf(t1.y, 0.f);
+              y[4] = fmaxf(t2.x, 0.f); y[5] = fmaxf(t2.y, 0.f); y[6] = fmaxf(t3.x, 0.f); y[7] = fmaxf(t3.y, 0.f);
               *reinterpret_cast<uint4*>(H + (hsel * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
             }
           }

@@ -139,6 +139,38 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2): two IEEE fp32 ops per issued instruction ----------
+// The CUDA-core phases of the kernels are issue-bound, so halving the instruction count of their FP work is a direct win.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // pack 8 fp32 -> 8 bf16 (round to nearest even) as one 16-byte chunk
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
