@@ -41,7 +41,7 @@ constexpr uint32_t kPatchBytes = 4 * kSlot;           // 4 K-quarters of the pat
 constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output) | patch k 0..127 | attention scratch
 constexpr uint32_t OFF_H = 32768;                  // 2 x 16 KB hidden chunks     | patch k 128..255 | attention scratch
 constexpr uint32_t OFF_AO = OFF_A;                 // 8 KB attention output operand [128 x 32]
-constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 = 51200 B (ends inside H)
+constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 + 16 B per clip = <= 51712 B (ends inside H)
 constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
 constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 5120
 constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 2 x 512 floats
@@ -102,9 +102,10 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const fl
 }
 
 // LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
-// `part` is double buffered by the caller (alternating halves) so that one barrier per LayerNorm suffices.
-__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, const float* gamma,
-                                              const float* beta, float eps, float* part, unsigned char* dst) {
+// Only the normalisation (x - mean) * rstd happens here: the affine part (gamma, beta) is folded into the weights
+// and bias of the Linear that consumes the operand when the weights are packed (W' = W diag(gamma), b' = b + W beta).
+__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part,
+                                              unsigned char* dst) {
   float mean, rstd;
   row_stats(tx, hsel, r, cb, eps, part, mean, rstd);
   const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
@@ -120,12 +121,8 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 c4 = *reinterpret_cast<const float4*>(cb + k0 + 4 * h);
-        const float4 g4 = *reinterpret_cast<const float4*>(gamma + k0 + 4 * h);
-        const float4 b4 = *reinterpret_cast<const float4*>(beta + k0 + 4 * h);
-        const float2 ya = fma2(fma2(add2(make_float2(v[c * 8 + 4 * h], v[c * 8 + 4 * h + 1]), make_float2(c4.x, c4.y)), rs2, nm2),
-                               make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-        const float2 yb = fma2(fma2(add2(make_float2(v[c * 8 + 4 * h + 2], v[c * 8 + 4 * h + 3]), make_float2(c4.z, c4.w)), rs2, nm2),
-                               make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+        const float2 ya = fma2(add2(make_float2(v[c * 8 + 4 * h], v[c * 8 + 4 * h + 1]), make_float2(c4.x, c4.y)), rs2, nm2);
+        const float2 yb = fma2(add2(make_float2(v[c * 8 + 4 * h + 2], v[c * 8 + 4 * h + 3]), make_float2(c4.z, c4.w)), rs2, nm2);
         y[4 * h + 0] = ya.x; y[4 * h + 1] = ya.y; y[4 * h + 2] = yb.x; y[4 * h + 3] = yb.y;
       }
       *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
@@ -326,16 +323,17 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       for (int blk = 0; blk < p.depth; ++blk) {
         mbar_wait_all(&bars[B_FULLP + ps], pphase);
         const float* prm = reinterpret_cast<const float*>(smem + OFF_PARAM + ps * kParamBytes);
-        const float *ln1_w = prm, *ln1_b = prm + 128, *cb1 = prm + 256, *qkv_b = prm + 384;
-        const float *ln2_w = prm + 512, *ln2_b = prm + 640, *cb2 = prm + 768, *b1 = prm + 896;
+        const float *cb1 = prm + 256, *qkv_b = prm + 384, *cb2 = prm + 768, *b1 = prm + 896;   // LN affine is folded into W/b
 
         // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
-        ln_to_operand(tx, hsel, r, cb1, ln1_w, ln1_b, 1e-6f, part, smem + OFF_A);            // stats buffer 0
+        ln_to_operand(tx, hsel, r, cb1, 1e-6f, part, smem + OFF_A);
         signal_ready();
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
         {   // qkv (+bias) -> fp32 scratch [128][100]
-          float* dstq = reinterpret_cast<float*>(smem + OFF_QKV) + r * QKV_LD + hsel * 48;
+          // rows of different clips are 24*400 B apart = the same banks: a 16-B pad per clip lets the two clips a warp
+          // straddles be served in one wavefront when the attention threads broadcast-read k/v rows
+          float* dstq = reinterpret_cast<float*>(smem + OFF_QKV) + r * QKV_LD + (r / tokens) * 4 + hsel * 48;
           const float* bq = qkv_b + hsel * 48;
           float v[32];
           tmem_ld32(tacc + hsel * 48, v);
@@ -363,11 +361,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 #pragma unroll
           for (int d = 0; d < 8; ++d) o2[d] = make_float2(0.f, 0.f);
           if (ar < rows_valid) {
-            const int base = (ar / tokens) * tokens;
+            const int clip = ar / tokens;
+            const int base = clip * tokens;
+            const float* qkv_c = qkv + clip * 4;              // per-clip pad (see the qkv epilogue)
             float qv[16];
 #pragma unroll
             for (int d = 0; d < 16; d += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(qkv + ar * QKV_LD + h * 16 + d);
+              const float4 t4 = *reinterpret_cast<const float4*>(qkv_c + ar * QKV_LD + h * 16 + d);
               qv[d] = t4.x; qv[d + 1] = t4.y; qv[d + 2] = t4.z; qv[d + 3] = t4.w;
             }
             float sc[UITK_MAX_TOKENS];
@@ -376,14 +376,15 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
               float a = 0.f;
               if (j < tokens) {
-                const float4* kj = reinterpret_cast<const float4*>(qkv + (base + j) * QKV_LD + 32 + h * 16);
+                const float4* kj = reinterpret_cast<const float4*>(qkv_c + (base + j) * QKV_LD + 32 + h * 16);
+                float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                   const float4 k4 = kj[d];
-                  a = fmaf(qv[4 * d], k4.x, a); a = fmaf(qv[4 * d + 1], k4.y, a);
-                  a = fmaf(qv[4 * d + 2], k4.z, a); a = fmaf(qv[4 * d + 3], k4.w, a);
+                  a2 = fma2(make_float2(qv[4 * d], qv[4 * d + 1]), make_float2(k4.x, k4.y), a2);
+                  b2 = fma2(make_float2(qv[4 * d + 2], qv[4 * d + 3]), make_float2(k4.z, k4.w), b2);
                 }
-                a *= 0.125f;
+                a = ((a2.x + a2.y) + (b2.x + b2.y)) * 0.125f;
                 mx = fmaxf(mx, a);
               }
               sc[j] = a;
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
               if (j < tokens) {
                 const float pj = sc[j] * inv;
                 const float2 pp = make_float2(pj, pj);
-                const float4* vj = reinterpret_cast<const float4*>(qkv + (base + j) * QKV_LD + 64 + h * 16);
+                const float4* vj = reinterpret_cast<const float4*>(qkv_c + (base + j) * QKV_LD + 64 + h * 16);
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                   const float4 v4 = vj[d];
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         tc_fence_after();
 
         // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
-        ln_to_operand(tx, hsel, r, cb2, ln2_w, ln2_b, 1e-6f, part + 512, smem + OFF_A);      // stats buffer 1
+        ln_to_operand(tx, hsel, r, cb2, 1e-6f, part + 512, smem + OFF_A);
         signal_ready();
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {

@@ -239,19 +239,29 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     if (cfg->precision == UITK_PREC_BF16) {
       unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();   // after the 4 x 16 KB patch chunks
       float* prm = reinterpret_cast<float*>(blk);
-      memcpy(prm + 0, b[0], 128 * 4); memcpy(prm + 128, b[1], 128 * 4);        // ln1 w, b
+      // LayerNorm affine folded into the consuming Linear: W' = W diag(gamma), b' = b + W beta (fp32, then bf16 for W')
+      std::vector<float> wq(96 * 128), w1f(384 * 128);
+      for (int o = 0; o < 96; ++o) {
+        float acc = b[3][o];
+        for (int k = 0; k < 128; ++k) { wq[o * 128 + k] = b[2][o * 128 + k] * b[0][k]; acc += b[2][o * 128 + k] * b[1][k]; }
+        prm[384 + o] = acc;                                                    // qkv bias'
+      }
+      for (int o = 0; o < 384; ++o) {
+        float acc = b[9][o];
+        for (int k = 0; k < 128; ++k) { w1f[o * 128 + k] = b[8][o * 128 + k] * b[6][k]; acc += b[8][o * 128 + k] * b[7][k]; }
+        prm[896 + o] = acc;                                                    // fc1 bias'
+      }
+      memcpy(prm + 0, b[0], 128 * 4); memcpy(prm + 128, b[1], 128 * 4);        // ln1 w, b (kept for reference; unused by the kernel)
       memcpy(prm + 256, cb.data(), 128 * 4);                                   // cb1
-      memcpy(prm + 384, b[3], 96 * 4);                                         // qkv bias (padded to 128)
-      memcpy(prm + 512, b[6], 128 * 4); memcpy(prm + 640, b[7], 128 * 4);      // ln2 w, b
+      memcpy(prm + 512, b[6], 128 * 4); memcpy(prm + 640, b[7], 128 * 4);      // ln2 w, b (unused by the kernel)
       for (int c = 0; c < 128; ++c) prm[768 + c] = cb[c] + b[5][c];            // cb2 = cb1 + proj bias
-      memcpy(prm + 896, b[9], 384 * 4);                                        // fc1 bias
       // weight chunks in the order the kernel consumes them (csrc/encoder_tc.cu)
       uint16_t* w = reinterpret_cast<uint16_t*>(blk + 1280 * 4);
-      pack_kmajor(w, b[2], 128, 0, 96, 0, 64); w += 96 * 64;                    // Wqkv [96][128], K half 0
-      pack_kmajor(w, b[2], 128, 0, 96, 64, 64); w += 96 * 64;                   // Wqkv, K half 1
+      pack_kmajor(w, wq.data(), 128, 0, 96, 0, 64); w += 96 * 64;               // Wqkv' [96][128], K half 0
+      pack_kmajor(w, wq.data(), 128, 0, 96, 64, 64); w += 96 * 64;              // Wqkv', K half 1
       pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // Wproj [128][32]
-      auto w1 = [&](int c) { pack_kmajor(w, b[8], 128, c * 64, 64, 0, 128); w += 64 * 128; };    // fc1 rows 64c..
-      auto w2 = [&](int c) { pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64; };   // fc2 K slice 64c..
+      auto w1 = [&](int c) { pack_kmajor(w, w1f.data(), 128, c * 64, 64, 0, 128); w += 64 * 128; };   // fc1' rows 64c..
+      auto w2 = [&](int c) { pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64; };        // fc2 K slice 64c..
       w1(0); w1(1); w2(0); w1(2); w2(1); w1(3); w2(2); w1(4); w2(3); w1(5); w2(4); w2(5);
     }
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
