@@ -39,6 +39,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel: str, arch: str, batch: int):
+    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/traffic.json), if it was taken
+    on this configuration; else None."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(p) or arch != "uit_xs" or batch != 4096:
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get(kernel, {}).get("traffic_bytes")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     FIELDS = ["clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
@@ -253,12 +264,34 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": {"kernel": "encoder (uitk_encoder)", "bound": "tensor", "achieved": enc_tflops,
                      "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": enc_tflops / peaks["bf16_tflops_sustained"],
-                     "traffic": None, "peak_source": peaks["source"] + " (bf16 cuBLAS, sustained)",
+                     "traffic": ncu_traffic("encoder_tc_kernel", args.arch, B) if args.precision == "bf16" else None,
+                     "traffic_unit": "bytes/launch (dram read+write, ncu)", "peak_source": peaks["source"] + " (bf16 cuBLAS, sustained)",
                      "ms_per_launch": ms_encoder, "flops_per_clip": flops},
         "roofline_frontend": {"kernel": "logmel_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                              "frac": fe_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                              "frac": fe_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("logmel_kernel", args.arch, B),
+                              "traffic_unit": "bytes/launch (dram read+write, ncu)", "peak_source": peaks["source"],
                               "ms_per_launch": ms_logmel, "bytes_per_clip": LOGMEL_BYTES_1S},
     }
+    # BASELINE config 4 (front-end alone on 10 s clips), bounded to 1024 clips so that the default run stays short
+    with torch.no_grad():
+        n10 = 1024
+        x10 = (0.1 * torch.randn(n10, 160000, generator=g, device=dev)).clamp_(-1, 1)       # 655 MB > L2
+        for _ in range(3):
+            model.front_end.logmel_unclamped(x10)
+        torch.cuda.synchronize()
+        f0, f1 = ev(), ev()
+        f0.record()
+        for _ in range(5):
+            model.front_end.logmel_unclamped(x10)
+        f1.record()
+        torch.cuda.synchronize()
+        ms10 = f0.elapsed_time(f1) / 5
+        bytes10 = 4 * 160000 + 4 * 64 * 1001
+        gbs10 = n10 * bytes10 / (ms10 * 1e-3) / 1e9
+        line["frontend_10s"] = {"workload": f"log-mel front-end alone, {n10} synthetic 10 s clips (BASELINE config 4, bounded)",
+                                "clips_per_s": n10 / (ms10 * 1e-3), "achieved": gbs10, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                "frac": gbs10 / peaks["hbm_gbs"], "bytes_per_clip": bytes10, "ms_per_launch": ms10}
+        del x10
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         xs = x_host[:CPU_SAMPLE_CLIPS].clone()
