@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 101
+#define UITK_VERSION 102
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
@@ -90,6 +90,11 @@ UITK_API int uitk_pack_frontend(const float* h_window, const float* h_fb, void* 
  *              afterwards that the clamp was inactive (min_db >= final max_db - 120) and the result therefore exact. */
 UITK_API int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const void* d_frontend_blob,
                 float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream);
+
+/* Same front-end on 16-bit PCM (x = pcm / 32768: the reference's own ingest normalisation, dataset.py:44-46 and
+ * torchaudio.load in inference.py:52).  Bit-identical to uitk_logmel on the converted floats; halves the input bytes. */
+UITK_API int uitk_logmel_i16(const int16_t* d_pcm, int64_t B, int64_t L, int64_t ld_pcm, const void* d_frontend_blob,
+                    float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream);
 
 /* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120). */
 UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream);

@@ -67,7 +67,7 @@ def assert_logmel_close(got, x, ref32):
 
 def test_library_loaded_is_in_tree():
     from uit_mobile_b200 import _native as N
-    assert N.lib().uitk_version() == 101
+    assert N.lib().uitk_version() == 102
     assert N.LIB_PATH.endswith("uit_mobile_b200/libuitk.so")
 
 
@@ -194,6 +194,26 @@ def test_batch_chunking_is_invisible():
         m.max_clips_per_launch = old
 
 
+def test_int16_pcm_ingest_is_bit_identical_to_float_path():
+    """int16 PCM in (x = pcm / 32768 in-kernel, the reference's ingest normalisation: dataset.py:44-46) gives exactly the
+    log-mel and scores of the float path on the converted samples; also through the host pipeline."""
+    from uit_mobile_b200.pipeline import HostPipeline
+    pcm, length, _ = H.samples_int16()
+    m = model("uit_xs", "trained", "bf16")
+    p16 = torch.from_numpy(pcm[:, :16000].copy())                       # [11, 16000] int16 (short files zero padded)
+    xf = p16.to(torch.float32) / 32768.0
+    db_i, mp_i = m.front_end.logmel_unclamped(p16.to(DEV))
+    db_f, mp_f = m.front_end.logmel_unclamped(xf.to(DEV))
+    assert torch.equal(db_i, db_f) and torch.equal(mp_i, mp_f)
+    assert torch.equal(m(p16.to(DEV)), m(xf.to(DEV)))
+    nat = torch.from_numpy(pcm[1:2, : int(length[1])].copy())           # 16 384 samples: 2-crop branch, odd alignment of rows
+    assert torch.equal(m(nat.to(DEV)), m((nat.to(torch.float32) / 32768.0).to(DEV)))
+    pipe = HostPipeline(m, 16, 16000, chunk=4, dtype=torch.int16)
+    assert torch.equal(pipe(p16.pin_memory()).clone(), m(xf.to(DEV)).cpu())
+    ref = H.load_golden("probs.npz")["uit_xs/trained/samples16k"]
+    assert np.abs(m(p16.to(DEV)).cpu().numpy() - ref).max() <= 2.5e-2
+
+
 def test_host_pipeline_matches_device_path_and_handles_q2():
     """HostPipeline (pinned host in/out, chunked, speculative per-chunk encode) == model(x) bit for bit, including the
     batch where the top-dB clamp is active (silent clip + loud clip => exact re-run with the final maximum)."""
@@ -211,6 +231,22 @@ def test_host_pipeline_matches_device_path_and_handles_q2():
     assert torch.equal(want, got)
     with pytest.raises(ValueError):
         pipe(torch.zeros(301, 16000).pin_memory())
+
+
+def test_infer_cli_runs_like_inference_py(tmp_path):
+    """infer.py (counterpart of the reference's inference.py) on two of the reference's sample clips, random-init weights."""
+    import subprocess, sys
+    from scipy.io import wavfile
+    pcm, length, names = H.samples_int16()
+    paths = []
+    for i in (0, 1):
+        p = tmp_path / names[i]
+        wavfile.write(p, 16000, pcm[i, : int(length[i])])
+        paths.append(str(p))
+    out = subprocess.run([sys.executable, H.REPO + "/infer.py", "-m", "uit_xxxs", "--random-init", "-k", "5", *paths],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("=====") == 4 and out.stdout.count("class ") + out.stdout.count("Keyword") >= 10
 
 
 def test_errors_are_loud():

@@ -41,6 +41,22 @@ int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wav, const 
                        reinterpret_cast<cudaStream_t>(stream));
 }
 
+int uitk_logmel_i16(const int16_t* d_pcm, int64_t B, int64_t L, int64_t ld_pcm, const void* d_frontend_blob, float* d_db,
+                    uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream) {
+  UITK_REQUIRE(d_pcm && d_frontend_blob && d_db && d_max_pow, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
+  UITK_REQUIRE(L > UITK_N_FFT / 2, UITK_EINVAL, "reflect padding needs L > 256 samples (got %lld)", (long long)L);
+  UITK_REQUIRE(L <= (1ll << 30), UITK_EINVAL, "clip too long (max 2^30 samples per row)");
+  UITK_REQUIRE(ld_pcm >= 1, UITK_EINVAL, "ld_pcm must be >= 1");
+  UITK_REQUIRE(aligned(d_pcm, 2) && aligned(d_db, 4) && aligned(d_max_pow, 4) && aligned(d_frontend_blob, 16), UITK_EALIGN,
+               "misaligned pointer");
+  if (B == 0) return UITK_OK;
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return launch_logmel_i16(d_pcm, B, L, ld_pcm, reinterpret_cast<const FrontendBlob*>(d_frontend_blob), d_db, d_max_pow, d_min_pow,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
 int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream) {
   UITK_REQUIRE(d_db && d_max_pow, UITK_EINVAL, "null pointer");
   UITK_REQUIRE(n >= 0, UITK_EINVAL, "negative size");

@@ -84,8 +84,12 @@ struct SmemLayout {
   // followed by mel_w[n_weights]
 };
 
+// TIn = float (the reference's input contract) or int16_t (PCM ingest: x = pcm / 32768, dataset.py:44-46 /
+// torchaudio.load normalisation; the 2^-15 scale is folded into the window, which is exact, so both instantiations
+// produce bit-identical results for the same audio).
+template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 3)
-logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
+logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
               const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
               uint32_t* __restrict__ min_pow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,13 +102,15 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
   const long long b = blockIdx.y;
   const int t_chunk0 = blockIdx.x * kChunk;
 
-  for (int i = tid; i < 512; i += kThreads) S.window[i] = blob->window[i];
+  constexpr bool kPcm = sizeof(TIn) == 2;
+  constexpr int kVec = 16 / (int)sizeof(TIn);          // samples per 16-byte cp.async
+  for (int i = tid; i < 512; i += kThreads) S.window[i] = kPcm ? blob->window[i] * (1.f / 32768.f) : blob->window[i];
   if (tid < 64) S.mel_lo[tid] = blob->mel_lo[tid];
   if (tid < 4) { S.mel_iters[tid] = blob->mel_iters[tid]; S.mel_qoff[tid] = blob->mel_qoff[tid]; }
   const int nw = blob->n_weights;
   for (int i = tid; i < nw; i += kThreads) s_melw[i] = blob->mel_w[i];
 
-  const float* clip = wav + b * ld;
+  const TIn* clip = wav + b * ld;
   float* out_clip = db + b * 64 * (long long)T;
   float tmax = 0.f, tmin = INFINITY;
   // thread-constant twiddles kept in registers: W256^(j*2^i) (the other powers are products of these) and W512^j
@@ -119,19 +125,19 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
     const int t0 = t_chunk0 + round * kFramesPerRound;
     if (round < kRounds && t0 < T) {
       const int s0 = t0 * UITK_HOP - UITK_N_FFT / 2;
-      float* dst = S.x[buf];
-      for (int i = tid * 4; i < kSamplesPerRound; i += kThreads * 4) {
+      TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
+      for (int i = tid * kVec; i < kSamplesPerRound; i += kThreads * kVec) {
         const int idx = s0 + i;
-        if (vec_ok && idx >= 0 && idx + 3 < Li) {
+        if (vec_ok && idx >= 0 && idx + kVec - 1 < Li) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(clip + idx)
                        : "memory");
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < kVec; ++e) {
             int id = idx + e;
             if (id < 0) id = -id;
             if (id >= Li) id = 2 * (Li - 1) - id;
-            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : 0.f;      // frames past T read zeros
+            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : TIn(0);      // frames past T read zeros
           }
         }
       }
@@ -146,15 +152,21 @@ logmel_kernel(const float* __restrict__ wav, long long L, long long ld, int T,
     stage(round + 1, (round + 1) & 1);                 // buffer last read two barriers ago
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();   // S.x[round & 1] (and the constants) visible; previous round's S.out readers are done
-    const float* sx = S.x[round & 1];
+    const TIn* sx = reinterpret_cast<const TIn*>(S.x[round & 1]);
 
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
     float2 v[16];
-    const float* xf = sx + g * UITK_HOP;
+    const TIn* xf = sx + g * UITK_HOP;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const int n = j + 16 * m;
-      const float2 xx = *reinterpret_cast<const float2*>(xf + 2 * n);
+      float2 xx;
+      if (kPcm) {
+        const short2 xs = *reinterpret_cast<const short2*>(xf + 2 * n);
+        xx = make_float2((float)xs.x, (float)xs.y);
+      } else {
+        xx = *reinterpret_cast<const float2*>(xf + 2 * n);
+      }
       const float2 ww = *reinterpret_cast<const float2*>(S.window + 2 * n);
       v[m] = make_float2(xx.x * ww.x, xx.y * ww.y);
     }
@@ -257,21 +269,32 @@ __global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint3
 
 }  // namespace
 
-int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
-                  uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
+template <typename TIn>
+static int launch_logmel_t(const TIn* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
+                           uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
   const int64_t T = 1 + L / UITK_HOP;
   const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
-  UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int chunks = (int)((T + kChunk - 1) / kChunk);
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int nb = (int)((B - b0) < 65535 ? (B - b0) : 65535);
     dim3 grid(chunks, nb);
-    logmel_kernel<<<grid, kThreads, smem, s>>>(wav + b0 * ld, (long long)L, (long long)ld, (int)T, blob,
-                                               db + b0 * 64 * T, max_pow, min_pow);
+    logmel_kernel<TIn><<<grid, kThreads, smem, s>>>(wav + b0 * ld, (long long)L, (long long)ld, (int)T, blob,
+                                                    db + b0 * 64 * T, max_pow, min_pow);
     count_launches(1);
   }
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;
+}
+
+int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
+                  uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
+  return launch_logmel_t<float>(wav, B, L, ld, blob, db, max_pow, min_pow, s);
+}
+
+int launch_logmel_i16(const int16_t* pcm, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
+                      uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
+  return launch_logmel_t<int16_t>(pcm, B, L, ld, blob, db, max_pow, min_pow, s);
 }
 
 int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, float top_db, cudaStream_t s) {

@@ -98,6 +98,8 @@ inline int time_patches_for(int64_t T, int target) {
 // kernels (launch wrappers), defined in the .cu files
 int launch_logmel(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
                   uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s);
+int launch_logmel_i16(const int16_t* pcm, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
+                      uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s);
 int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, float top_db, cudaStream_t s);
 
 struct EncoderArgs {

@@ -188,8 +188,8 @@ class FrontEnd(nn.Sequential):
         pipelined caller write chunks of one batch into a shared buffer and keep ONE running maximum (Q2)."""
         if not x.is_cuda:
             raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
-        if x.dtype != torch.float32:
-            raise N.UitkError(f"expected float32 waveform, got {x.dtype}")
+        if x.dtype not in (torch.float32, torch.int16):
+            raise N.UitkError(f"expected a float32 waveform (or int16 PCM), got {x.dtype}")
         if B is None:
             if x.dim() != 2:
                 raise ValueError(f"expected a [B, L] waveform batch, got shape {tuple(x.shape)}")
@@ -206,9 +206,10 @@ class FrontEnd(nn.Sequential):
         if max_pow is None:
             max_pow = torch.zeros(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
-            N.check(l.uitk_logmel(x.data_ptr(), B, L, ld, self._blob(x.device).data_ptr(), out.data_ptr(),
-                                  max_pow.data_ptr(), None if min_pow is None else min_pow.data_ptr(),
-                                  torch.cuda.current_stream(x.device).cuda_stream), "uitk_logmel")
+            fn = l.uitk_logmel_i16 if x.dtype == torch.int16 else l.uitk_logmel     # PCM: x = pcm / 32768 in-kernel
+            N.check(fn(x.data_ptr(), B, L, ld, self._blob(x.device).data_ptr(), out.data_ptr(),
+                       max_pow.data_ptr(), None if min_pow is None else min_pow.data_ptr(),
+                       torch.cuda.current_stream(x.device).cuda_stream), "uitk_logmel")
         return out, max_pow
 
 

@@ -32,7 +32,7 @@ def _bits_to_db(bits: int) -> float:
 
 class HostPipeline:
     def __init__(self, model, max_batch: int, L: int = 16000, chunk: int = 1024, device: Optional[torch.device] = None,
-                 speculative: bool = True):
+                 speculative: bool = True, dtype: torch.dtype = torch.float32):
         self.model = model
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
@@ -41,7 +41,10 @@ class HostPipeline:
         self.speculative = speculative
         T = int(N.lib().uitk_num_frames(L))
         dev = self.device
-        self.stage = [torch.empty((self.chunk, L), dtype=torch.float32, device=dev) for _ in range(2)]
+        if dtype not in (torch.float32, torch.int16):
+            raise ValueError("dtype must be float32 (reference contract) or int16 (PCM ingest, x = pcm / 32768)")
+        self.dtype = dtype
+        self.stage = [torch.empty((self.chunk, L), dtype=dtype, device=dev) for _ in range(2)]
         self.db = torch.empty((max_batch, 64, T), dtype=torch.float32, device=dev)
         self.words = torch.zeros(2, dtype=torch.int32, device=dev)          # [max power bits, min power bits]
         self.probs = torch.empty((max_batch, model.outputdim), dtype=torch.float32, device=dev)
@@ -56,8 +59,8 @@ class HostPipeline:
     @torch.no_grad()
     def __call__(self, wav_host: torch.Tensor) -> torch.Tensor:
         """wav_host: pinned float32 [B, L] host tensor.  Returns a pinned host view [B, outputdim]."""
-        if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 2 or wav_host.shape[1] != self.L:
-            raise ValueError(f"expected a host float32 [B, {self.L}] tensor")
+        if wav_host.is_cuda or wav_host.dtype != self.dtype or wav_host.dim() != 2 or wav_host.shape[1] != self.L:
+            raise ValueError(f"expected a host {self.dtype} [B, {self.L}] tensor")
         B = wav_host.shape[0]
         if B > self.max_batch:
             raise ValueError(f"batch {B} exceeds the pipeline capacity {self.max_batch}")
@@ -104,6 +107,6 @@ class HostPipeline:
                 m.encode(self.db[:B], max_w, out=self.probs[:B])
                 out.copy_(self.probs[:B], non_blocking=True)
                 main.synchronize()
-        self.h2d_bytes = B * self.L * 4
+        self.h2d_bytes = B * self.L * wav_host.element_size()
         self.d2h_bytes = B * m.outputdim * 4 + 8
         return out
