@@ -18,8 +18,9 @@ x[0] = 0.0                                               # silent clip on rank 0
 x[-1] = (0.9 * torch.randn(16000, generator=g)).clamp_(-1, 1)   # ... the loudest one on the last rank
 with torch.no_grad():
     ref = model(x.to(dev))                               # single-GPU, whole batch
-    b, e = sharding.shard_bounds(total, rank, world)
-    got = sharding.sharded_forward(model, x[b:e].to(dev), total)
+    align = model.tile_clips(101)                        # tile-aligned shards: bit-identical to the single-GPU run
+    b, e = sharding.shard_bounds(total, rank, world, align)
+    got = sharding.sharded_forward(model, x[b:e].to(dev), total, align=align)
 ok = torch.equal(ref, got)
 t = torch.tensor([int(ok)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

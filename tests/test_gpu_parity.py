@@ -171,10 +171,11 @@ def test_fp32_vs_oracle_large_seeded_batch():
 
 def test_shard_invariance_single_gpu():
     """Two half-batches that share the all-reduced max word reproduce the full-batch scores bit for bit."""
-    m = model("uit_xxs")
-    x = torch.from_numpy(INPUTS["adversarial"]).to(DEV)
+    m = model("uit_xxs", "trained", "bf16")
+    x = torch.from_numpy(np.concatenate([H.noise_clips(5, seed=41, amp=1e-3), INPUTS["adversarial"]])).to(DEV)
     full = m(x)
-    a, b = x[:2].contiguous(), x[2:].contiguous()
+    assert m.tile_clips(101) == 5
+    a, b = x[:5].contiguous(), x[5:].contiguous()      # shard boundary on a tile boundary (sharding.shard_bounds(align=5))
     db_a, mp_a = m.front_end.logmel_unclamped(a)
     db_b, mp_b = m.front_end.logmel_unclamped(b)
     mp = torch.maximum(mp_a, mp_b)

@@ -21,6 +21,12 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         S.shard_bounds(10, 2, 2)
+    for total in (7, 131, 4096, 65536):                      # tile-aligned shards (5 clips per 128-row tile)
+        for world in (2, 3, 8):
+            spans = [S.shard_bounds(total, r, world, align=5) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(b % 5 == 0 or b == total for b, _ in spans)
 
 
 def test_window_shards_cover_stream_with_halo():

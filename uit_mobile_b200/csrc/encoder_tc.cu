@@ -42,6 +42,11 @@ constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN outpu
 constexpr uint32_t OFF_H = 32768;                  // 2 x 16 KB hidden chunks     | patch k 128..255 | attention scratch
 constexpr uint32_t OFF_AO = OFF_A;                 // 8 KB attention output operand [128 x 32]
 constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 + 16 B per clip = <= 51712 B (ends inside H)
+// tensor-core attention operands (tokens == 24), all inside A|H which are idle between the qkv and proj GEMMs
+constexpr uint32_t OFF_Q = OFF_A + 8192;           // Q_h  [128 x 16] bf16 K-major, head h at + h*4096
+constexpr uint32_t OFF_K = OFF_A + 16384;          // K_h  [128 x 16] (B operand: N = key row)
+constexpr uint32_t OFF_VT = OFF_A + 24576;         // V_h^T [16 x 128] (B operand: N = d, K = key row; k-group stride 256 B)
+constexpr uint32_t OFF_P = OFF_H;                  // P_h  [128 x 128] bf16 K-major (block diagonal, zeros elsewhere), 32 KB
 constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
 constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 5120
 constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 2 x 512 floats
@@ -62,6 +67,7 @@ struct TcParams {
   int RR, G, num_tiles, depth;
   float* pooled;   // [RR][128]
   float* dbg_x;    // optional [RR*tokens][128]: residual stream after the last block (pre final LN)
+  int tc_attn;     // 1: attention GEMMs on tcgen05 (needs tokens == 24); 0: CUDA-core attention
 };
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     if (lane == 0) {
       const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
       constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
+      constexpr uint32_t ID16 = make_idesc_bf16(128, 16);
+      const bool tc_attn = p.tc_attn != 0;
       uint32_t cslot = 0, cphase = 0, sig = 0;
       auto wait_ready = [&]() {
         mbar_wait(&bars[B_READY + (sig & 1)], (sig >> 1) & 1);
@@ -210,6 +218,19 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           mma_from_ring(tmem + 128, sA, ID96, 1536, 4, false);
           mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, 4, true);
           umma_commit(&bars[B_ACC]);
+          if (tc_attn) {                                                      // attention GEMMs (no weights involved)
+            for (int h = 0; h < 2; ++h) {
+              wait_ready();                                                   // Q/K/V^T operands written (h=0) / ACC drained (h=1)
+              umma_bf16(tmem + 128, make_smem_desc(smem_u32(smem + OFF_Q) + h * 4096, 2048, 128),
+                        make_smem_desc(smem_u32(smem + OFF_K) + h * 4096, 2048, 128), ID128, 0u);          // S_h = Q_h K_h^T
+              umma_commit(&bars[B_ACC]);
+              wait_ready();                                                   // P_h written, S_h consumed
+              for (int ks = 0; ks < 8; ++ks)                                  // O_h = P_h V_h  (N = 16, K = 128)
+                umma_bf16(tmem + 128, make_smem_desc(smem_u32(smem + OFF_P) + ks * 4096, 2048, 128),
+                          make_smem_desc(smem_u32(smem + OFF_VT) + h * 4096 + ks * 512, 256, 128), ID16, ks > 0 ? 1u : 0u);
+              umma_commit(&bars[B_ACC]);
+            }
+          }
           wait_ready();                                                       // attention output in A_o
           mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, 2, true);         // x += o Wproj^T (bias deferred into cb2)
           umma_commit(&bars[B_X]);
@@ -330,6 +351,113 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         signal_ready();
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
+        if (p.tc_attn) {
+          // ---------- tensor-core attention: S_h = Q_h K_h^T and O_h = P_h V_h on tcgen05, softmax straight from TMEM ----------
+          const bool valid = r < rows_valid;
+          const int g = valid ? r / 24 : 0;
+          const int cbase = g * 24;                                   // this row's keys = S columns [cbase, cbase + 24)
+          {   // qkv (+bias) -> bf16 operands.  hsel 0 holds q(32) k_h0(16); hsel 1 holds k_h1(16) v(32)
+            const float* bq = qkv_b + hsel * 48;
+            float v[32], w[16];
+            tmem_ld32(tacc + hsel * 48, v);
+            tmem_ld16(tacc + hsel * 48 + 32, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bq + 32 + i);
+              w[i] += b4.x; w[i + 1] += b4.y; w[i + 2] += b4.z; w[i + 3] += b4.w;
+            }
+            if (hsel == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)                               // q: head c>>1, k-group c&1
+                *reinterpret_cast<uint4*>(smem + OFF_Q + (c >> 1) * 4096 + (c & 1) * 2048 + r * 16) = pack8_bf16(v + c * 8);
+#pragma unroll
+              for (int c = 0; c < 2; ++c)                               // k, head 0
+                *reinterpret_cast<uint4*>(smem + OFF_K + c * 2048 + r * 16) = pack8_bf16(w + c * 8);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)                               // k, head 1
+                *reinterpret_cast<uint4*>(smem + OFF_K + 4096 + c * 2048 + r * 16) = pack8_bf16(v + c * 8);
+              unsigned char* vt = smem + OFF_VT + (r >> 3) * 256 + (r & 7) * 2;      // V^T[d][key r]
+#pragma unroll
+              for (int d = 0; d < 16; ++d) {
+                *reinterpret_cast<__nv_bfloat16*>(vt + d * 16) = __float2bfloat16_rn(v[16 + d]);            // head 0
+                *reinterpret_cast<__nv_bfloat16*>(vt + 4096 + d * 16) = __float2bfloat16_rn(w[d]);          // head 1
+              }
+            }
+          }
+          signal_ready();
+          constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // softmax(0.125 * s) through exp2
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // S_h in ACC
+            tc_fence_after();
+            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp straddle two clips: load the
+            // key window of each of the two clips in turn and let every lane keep the one that belongs to its row
+            float sv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+            const int g_lo = (q * 32) / 24;                              // clip of the warp's first row (warp-uniform)
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const int gg = g_lo + pass;
+              if (gg <= 4) {
+                float t[16];
+                if (hsel == 0) { tmem_ld8(tacc + gg * 24, t); tmem_ld8(tacc + gg * 24 + 8, t + 8); }
+                else { tmem_ld8(tacc + gg * 24 + 16, t); }
+                tmem_ld_wait();
+                if (valid && g == gg) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) sv[i] = t[i];
+                }
+              }
+            }
+            const int n = hsel == 0 ? 16 : 8;
+            float m_loc = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < n) m_loc = fmaxf(m_loc, sv[i]);
+            float l_loc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < n) { sv[i] = exp2f((sv[i] - m_loc) * kScaleLog2e); l_loc += sv[i]; }
+            float* ex = part + h * 512;
+            *reinterpret_cast<float2*>(ex + (hsel * 128 + r) * 2) = make_float2(m_loc, l_loc);
+            bar_compute();
+            const float2 oth = *reinterpret_cast<const float2*>(ex + ((hsel ^ 1) * 128 + r) * 2);
+            const float M = fmaxf(m_loc, oth.x);
+            const float f_own = exp2f((m_loc - M) * kScaleLog2e), f_oth = exp2f((oth.x - M) * kScaleLog2e);
+            const float f = valid ? f_own / (l_loc * f_own + oth.y * f_oth) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] *= f;
+            unsigned char* P = smem + OFF_P + r * 16;
+            const int c0 = valid ? 3 * g : 99;                            // value chunks c0 .. c0+2 (none for padding rows)
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int kk = hsel * 8 + k8;
+              if (kk < c0 || kk > c0 + 2) *reinterpret_cast<uint4*>(P + kk * 2048) = make_uint4(0, 0, 0, 0);
+            }
+            if (valid) {
+              if (hsel == 0) {
+                *reinterpret_cast<uint4*>(P + c0 * 2048) = pack8_bf16(sv);
+                *reinterpret_cast<uint4*>(P + (c0 + 1) * 2048) = pack8_bf16(sv + 8);
+              } else {
+                *reinterpret_cast<uint4*>(P + (c0 + 2) * 2048) = pack8_bf16(sv);
+              }
+            }
+            signal_ready();                                               // P_h complete, S_h consumed
+            mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // O_h in ACC columns 0..15
+            tc_fence_after();
+            float o[8];
+            tmem_ld8(tacc + hsel * 8, o);
+            tmem_ld_wait();
+            *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + hsel) * 2048 + r * 16) = pack8_bf16(o);
+            if (h == 0) signal_ready();                                   // ACC drained: S_1 may overwrite it
+          }
+        } else {
         {   // qkv (+bias) -> fp32 scratch [128][100]
           // rows of different clips are 24*400 B apart = the same banks: a 16-B pad per clip lets the two clips a warp
           // straddles be served in one wavefront when the attention threads broadcast-read k/v rows
@@ -414,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           const float* out = reinterpret_cast<const float*>(o2);
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 0) * 2048 + ar * 16) = pack8_bf16(out);
           *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 1) * 2048 + ar * 16) = pack8_bf16(out + 8);
+        }
         }
         signal_ready();
         mbar_wait_all(&bars[B_X], ph_x); ph_x ^= 1;
@@ -550,7 +679,8 @@ int run_encoder_tc(const EncoderArgs& a) {
   p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
   p.RR = (int)RR; p.G = 128 / tokens; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;
   p.pooled = pooled;
-  p.dbg_x = a.debug_taps ? dbg_x : nullptr;
+  p.dbg_x = (a.debug_taps & 1) ? dbg_x : nullptr;
+  p.tc_attn = (tokens == 24 && !(a.debug_taps & 2)) ? 1 : 0;     // debug bit 1 forces the CUDA-core attention
 
   int dev = 0, sms = 0;
   UITK_CHECK_CUDA(cudaGetDevice(&dev));

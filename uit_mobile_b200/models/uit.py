@@ -343,7 +343,11 @@ class UITBase(nn.Module):
             if tuple(out.shape) != (B, self.outputdim) or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError("out must be a contiguous float32 [B, outputdim] tensor")
             probs = out
-        step = max(1, self.max_clips_per_launch // int(l.uitk_num_crops(T, self.target_length)))
+        # launches are cut at multiples of the kernel's 128-row tile (5 clip-crops of 24 tokens): the tensor-core attention
+        # sums over a tile's keys, so a clip's rounding depends on its position inside the tile; tile-aligned cuts keep
+        # chunked / sharded runs bit-identical to a single launch
+        tile = self.tile_clips(T)
+        step = max(tile, self.max_clips_per_launch // int(l.uitk_num_crops(T, self.target_length)) // tile * tile)
         stream = torch.cuda.current_stream(db.device).cuda_stream
         with torch.cuda.device(db.device):
             ws = None
@@ -359,6 +363,17 @@ class UITBase(nn.Module):
                                        ws.data_ptr(), ws.numel(), stream), "uitk_encoder")
             self._last_workspace = ws
         return probs
+
+    def tile_clips(self, T: int) -> int:
+        """Clips per 128-row encoder tile for T frames: chunk / shard boundaries that are multiples of this (in clips)
+        reproduce a single launch bit for bit."""
+        l = N.lib()
+        rows_per_clip = int(l.uitk_num_crops(T, self.target_length)) * int(l.uitk_tokens_per_crop(T, self.target_length))
+        per_tile = 128 // int(l.uitk_tokens_per_crop(T, self.target_length))          # clip-crops per tile
+        crops = int(l.uitk_num_crops(T, self.target_length))
+        # smallest number of clips whose clip-crops fill whole tiles
+        import math
+        return per_tile // math.gcd(per_tile, crops) if rows_per_clip else 1
 
     def forward(self, x: torch.Tensor, mixup=None) -> torch.Tensor:
         if self.training:

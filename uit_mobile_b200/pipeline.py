@@ -37,7 +37,10 @@ class HostPipeline:
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise N.UitkError("HostPipeline needs the model on a CUDA device (no CPU fallback)")
-        self.max_batch, self.L, self.chunk = max_batch, L, min(chunk, max_batch)
+        T0 = int(N.lib().uitk_num_frames(L))
+        tile = model.tile_clips(T0)                      # tile-aligned chunks keep the result bit-identical to one launch
+        self.max_batch, self.L = max_batch, L
+        self.chunk = max(tile, min(chunk, max_batch) // tile * tile)
         self.speculative = speculative
         T = int(N.lib().uitk_num_frames(L))
         dev = self.device

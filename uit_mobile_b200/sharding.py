@@ -16,13 +16,19 @@ import torch
 import torch.distributed as dist
 
 
-def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous [begin, end) of ``total`` clips owned by ``rank``; the first ``total % world`` ranks get one more."""
+def shard_bounds(total: int, rank: int, world: int, align: int = 1) -> Tuple[int, int]:
+    """Contiguous [begin, end) of ``total`` clips owned by ``rank``; the first ranks get the remainder.
+
+    ``align`` > 1 makes every boundary (except the end) a multiple of ``align`` clips: with ``align =
+    model.tile_clips(T)`` every clip keeps the position inside its 128-row encoder tile that it has in a single-GPU
+    run, which makes the sharded scores bit-identical to the single-GPU ones."""
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside world of {world}")
-    base, rem = divmod(total, world)
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    units = -(-total // align)                       # ceil: the last unit may be ragged
+    base, rem = divmod(units, world)
+    ub = rank * base + min(rank, rem)
+    ue = ub + base + (1 if rank < rem else 0)
+    return min(ub * align, total), min(ue * align, total)
 
 
 def window_shard_bounds(n_windows: int, hop: int, win: int, rank: int, world: int) -> Tuple[int, int, int, int]:
@@ -42,11 +48,11 @@ def allreduce_max_word(word: torch.Tensor, group=None) -> torch.Tensor:
     return word
 
 
-def gather_scores(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+def gather_scores(local: torch.Tensor, total: int, group=None, align: int = 1) -> torch.Tensor:
     """All-gather per-rank score slices ``[n_r, C]`` (n_r from ``shard_bounds``) into ``[total, C]`` on every rank."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    sizes = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
+    sizes = [shard_bounds(total, r, world, align)[1] - shard_bounds(total, r, world, align)[0] for r in range(world)]
     if local.shape[0] != sizes[rank]:
         raise ValueError(f"rank {rank} holds {local.shape[0]} rows, expected {sizes[rank]}")
     C = local.shape[1]
@@ -62,9 +68,9 @@ def gather_scores(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     return torch.cat([p[:n] for p, n in zip(parts, sizes)])
 
 
-def sharded_forward(model, wav_local: torch.Tensor, total: int, group=None, gather: bool = True) -> torch.Tensor:
+def sharded_forward(model, wav_local: torch.Tensor, total: int, group=None, gather: bool = True, align: int = 1) -> torch.Tensor:
     """Run the model on this rank's slice and (optionally) gather all scores.  ``model.process_group`` is set so
-    that the top-dB scope is the global batch."""
+    that the top-dB scope is the global batch.  ``align`` must be the value used for ``shard_bounds``."""
     model.process_group = group if group is not None else dist.group.WORLD
     local = model(wav_local)
-    return gather_scores(local, total, group) if gather else local
+    return gather_scores(local, total, group, align) if gather else local
