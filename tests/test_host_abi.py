@@ -60,7 +60,7 @@ def test_frontend_pack_layout(lib):
         q, j = divmod(m, 16)
         for i in range(iters[q]):
             dense[lo[m] + 4 * i: lo[m] + 4 * i + 4, m] = w[qoff[q] + (i * 16 + j) * 4: qoff[q] + (i * 16 + j) * 4 + 4]
-    np.testing.assert_array_equal(dense[:257], fb.numpy())
+    np.testing.assert_array_equal(dense[:257], 0.25 * fb.numpy())      # weights carry the 1/4 of the kernel's 4|X|^2
     assert (dense[257:] == 0).all()
     # error path: blob too small
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, 16) == -5

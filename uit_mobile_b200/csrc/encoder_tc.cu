@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_READY || i == B_READY + 1) ? kCompute : 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_READY || i == B_READY + 1) ? kCompute / 32 : 1);   // one arrive per compute warp
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -262,10 +262,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     uint32_t ph_acc = 0, ph_x = 0, ph_fc1[2] = {0, 0}, ph_h[2] = {0, 0};
     uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
     // operand written by this thread is visible to the async proxy, its TMEM reads are done: tell the MMA issuer
+    // (every thread fences its own writes; __syncwarp orders the warp; ONE lane arrives -> 8 arrivals per signal instead
+    // of 256 serialized shared-memory atomics)
     auto signal_ready = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bars[B_READY + (sig & 1)]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_READY + (sig & 1)]);
       ++sig;
     };
 

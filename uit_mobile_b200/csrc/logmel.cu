@@ -10,6 +10,7 @@
 // shared memory (warp-synchronous, padded rows), second radix-16 pass, real-FFT unpack, |X|^2, sparse mel
 // (<=2 non-zero filters per bin -> packed ranges), dB.  HBM sees every sample once (frames overlap 3.2x; the
 // overlap is absorbed by the staging buffer / L1) and every output once: 4*L + 4*64*T algorithmic bytes/clip.
+#include "tc_ptx.cuh"
 #include "uitk_common.cuh"
 
 namespace uitk {
@@ -34,17 +35,22 @@ __device__ constexpr float kSin32[16] = {0.f, 0.19509032201612827f, 0.3826834323
                                          0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960222f,
                                          0.38268343236508977f, 0.19509032201612827f};
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex arithmetic on packed fp32x2 (FADD2 / FMUL2 / FFMA2): a complex add is ONE instruction, a complex multiply TWO
+// (ptxas folds the (x,x) / (y,y) broadcasts and the (-w.y, w.x) swizzle into operand selectors).
+using tc::add2; using tc::fma2; using tc::mul2; using tc::sub2;
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return fma2(make_float2(a.y, a.y), make_float2(-w.y, w.x), mul2(make_float2(a.x, a.x), w));
 }
 
 // forward radix-4 butterfly (e^{-2 pi i nk/4})
 __device__ __forceinline__ void fft4(float2& a, float2& b, float2& c, float2& d) {
-  float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d);
-  float2 t3 = make_float2(b.y - d.y, d.x - b.x);   // (b - d) * (-i)
-  a = cadd(t0, t2); b = cadd(t1, t3); c = csub(t0, t2); d = csub(t1, t3);
+  const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), u = csub(b, d);
+  const float2 us = make_float2(u.y, u.x);                        // (b - d) * (-i) = (u.y, -u.x)
+  a = cadd(t0, t2); c = csub(t0, t2);
+  b = fma2(us, make_float2(1.f, -1.f), t1);
+  d = fma2(us, make_float2(-1.f, 1.f), t1);
 }
 
 // in-register forward 16-point DFT, natural order in and out
@@ -168,7 +174,7 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
         xx = *reinterpret_cast<const float2*>(xf + 2 * n);
       }
       const float2 ww = *reinterpret_cast<const float2*>(S.window + 2 * n);
-      v[m] = make_float2(xx.x * ww.x, xx.y * ww.y);
+      v[m] = mul2(xx, ww);
     }
     fft16(v);                                   // over m -> k1
     {   // v[k1] *= W256^(j*k1), powers composed from w1, w2, w4, w8 (<= 3 roundings)
@@ -191,7 +197,10 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
     // ---- real-FFT unpack + power: X[k] = E[k] + W512^k O[k], k = j + 16 m.  The partner Z[256-k] lives in lane
     // (16-j) of this frame group at register 15-m (lane 0: its own register (16-m)&15): one shuffle, static indices.
     // W512^k = W512^j * W32^m with W32^m compile-time constants.
+    // 2 X[k] = (A + B) + G (A - B) with A = Z[k], B = conj(Z[256-k]), G = -i W512^k; G[m+1] = G[m] * W32 (<= 16 roundings).
+    // The factor 1/4 of |X|^2 is folded into the packed mel weights (exact: power of two).
     float p[16];
+    float2 G = make_float2(wj512.y, -wj512.x);                     // -i * W512^j
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const float2 zk = v[m];
@@ -199,19 +208,18 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
       zn.x = __shfl_sync(0xffffffffu, v[15 - m].x, (16 - j) & 15, 16);
       zn.y = __shfl_sync(0xffffffffu, v[15 - m].y, (16 - j) & 15, 16);
       if (j == 0) zn = v[(16 - m) & 15];
-      const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
-      const float orr = 0.5f * (zk.y + zn.y), oi = -0.5f * (zk.x - zn.x);
-      const float2 w = cmul(wj512, make_float2(kCos32[m], -kSin32[m]));
-      const float xr = er + (orr * w.x - oi * w.y);
-      const float xi = ei + (orr * w.y + oi * w.x);
-      p[m] = xr * xr + xi * xi;
+      const float2 S2 = fma2(zn, make_float2(1.f, -1.f), zk);     // A + B
+      const float2 D2 = fma2(zn, make_float2(-1.f, 1.f), zk);     // A - B
+      const float2 X2 = cadd(S2, cmul(D2, G));
+      p[m] = fmaf(X2.x, X2.x, X2.y * X2.y);                       // 4 |X[k]|^2
+      G = cmul(G, make_float2(kCos32[1], -kSin32[1]));
     }
     __syncwarp();
     float* pf = reinterpret_cast<float*>(e);
 #pragma unroll
     for (int m = 0; m < 16; ++m) pf[j + 16 * m] = p[m];
     if (j == 0) {
-      const float ny = v[0].x - v[0].y;         // X[256] = Re Z0 - Im Z0
+      const float ny = 2.f * (v[0].x - v[0].y);   // X[256] = Re Z0 - Im Z0 (x2: powers are kept as 4 |X|^2)
       pf[256] = ny * ny;
     }
     __syncwarp();

@@ -147,7 +147,8 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
       for (int j = 0; j < 16; ++j)
         for (int e = 0; e < 4; ++e) {
           const int m = 16 * q + j, k = lo_[m] + 4 * i + e;
-          fb->mel_w[n + (i * 16 + j) * 4 + e] = (k <= hi_[m] && k < UITK_N_FREQS) ? h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
+          // x 1/4: the kernel keeps the power spectrum as 4 |X|^2 (exact scaling)
+          fb->mel_w[n + (i * 16 + j) * 4 + e] = (k <= hi_[m] && k < UITK_N_FREQS) ? 0.25f * h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
         }
     n += iters * 64;
   }
