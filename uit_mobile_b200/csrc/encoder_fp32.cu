@@ -12,7 +12,7 @@ namespace uitk {
 namespace {
 
 enum { PRO_PLAIN = 0, PRO_LN = 1, PRO_PATCH = 2 };
-enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESID = 2, EPI_PATCH = 3 };
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESID = 2, EPI_PATCH = 3, EPI_SIGMOID = 4 };
 
 struct GemmParams {
   const float* A; int lda;
@@ -20,6 +20,7 @@ struct GemmParams {
   const float* bias;
   float* C; int ldc;
   int M, K;
+  int n_valid;   // EPI_SIGMOID: columns >= n_valid are padding and are not stored
   // PRO_LN
   const float* ln_w; const float* ln_b; float ln_eps;
   // PRO_PATCH / EPI_PATCH
@@ -149,6 +150,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
     for (int j = 0; j < TN; ++j) {
       const int col = n0 + tx + 16 * j;
       float v = acc[i][j] + p.bias[col];
+      if (EPI == EPI_SIGMOID) {
+        if (col < p.n_valid) p.C[(size_t)row * p.ldc + col] = 1.f / (1.f + expf(-v));
+        continue;
+      }
       if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
       if (EPI == EPI_PATCH) { v += p.time_pos[tau * 128 + col]; v += p.freq_pos[f * 128 + col]; }
       float* dst = p.C + (size_t)row * p.ldc + col;
@@ -452,6 +457,18 @@ __global__ void __launch_bounds__(256) head_pooled_kernel(const float* __restric
 
 int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim,
                        int eval_max, float* probs, cudaStream_t s) {
+  if (crops == 1 && B < (1ll << 31) - 256) {
+    // single crop: one tiled fp32 GEMM [B,128] x [128,outputdim] with the head LayerNorm as prologue and the sigmoid as
+    // epilogue (every weight tile fetched from L2 feeds 128 clips)
+    GemmParams g{};
+    g.M = (int)B; g.K = 128; g.A = pooled; g.lda = 128; g.Wt = W + lay.head_wt; g.ldw = lay.outputdim_padded;
+    g.bias = W + lay.head_b; g.C = probs; g.ldc = outputdim; g.n_valid = outputdim;
+    g.ln_w = W + lay.hln_w; g.ln_b = W + lay.hln_b; g.ln_eps = 1e-5f;
+    gemm_kernel<128, PRO_LN, EPI_SIGMOID><<<dim3((unsigned)((B + BM - 1) / BM), lay.outputdim_padded / 128), 256, 0, s>>>(g);
+    count_launches(1);
+    UITK_CHECK_CUDA(cudaGetLastError());
+    return UITK_OK;
+  }
   head_pooled_kernel<<<(unsigned)((B + kHeadClips - 1) / kHeadClips), 256, 0, s>>>(
       pooled, (long long)B, crops, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded,
       eval_max, probs);

@@ -33,7 +33,7 @@ static size_t take(size_t& cur, size_t n) {
 EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
   EncoderLayout l{};
   l.depth = depth; l.outputdim = outputdim; l.grid_t = grid_t;
-  l.outputdim_padded = (outputdim + 3) / 4 * 4;
+  l.outputdim_padded = (outputdim + 127) / 128 * 128;   // zero-padded to whole 128-column GEMM tiles
   size_t cur = 0;
   l.bn_scale = take(cur, 64); l.bn_shift = take(cur, 64);
   l.patch_wt = take(cur, 256 * 128); l.patch_b = take(cur, 128);
