@@ -250,6 +250,15 @@ def test_infer_cli_runs_like_inference_py(tmp_path):
     assert out.stdout.count("=====") == 4 and out.stdout.count("class ") + out.stdout.count("Keyword") >= 10
 
 
+def test_empty_and_single_clip_batches():
+    m = model("uit_xxxs", "trained", "bf16")
+    assert tuple(m(torch.zeros(0, 16000, device=DEV)).shape) == (0, 537)
+    x = torch.from_numpy(H.noise_clips(6, seed=3)).to(DEV)
+    full = m(x)
+    one = m(x[:1].contiguous())                   # B = 1: a single ragged tile; clip 0 sits at tile position 0 in both runs
+    assert torch.equal(one[0], full[0])
+
+
 def test_errors_are_loud():
     from uit_mobile_b200 import _native as N
     m = model("uit_xxxs")

@@ -103,6 +103,18 @@ def test_module_contract():
         assert sum(p.numel() for p in m.parameters()) == {"uit_xs": 1495577, "uit_xxs": 799961, "uit_xxxs": 568089}[arch]
 
 
+def test_tile_clips_and_fused_stage_methods(lib):
+    import uit_mobile_b200 as U
+    m = U.models.uit_xxxs(outputdim=537, target_length=102)
+    assert m.tile_clips(101) == 5            # 1 s clip: 24 tokens -> 5 clips per 128-row tile
+    assert m.tile_clips(1001) == 1           # 10 s clip: 10 crops of 24 tokens -> tiles already cut at clip boundaries? (gcd rule)
+    assert m.tile_clips(16) == 32            # 2400 samples: 4 tokens
+    with pytest.raises(NotImplementedError):
+        m.forward_features(torch.zeros(1, 1, 64, 102))
+    with pytest.raises(NotImplementedError):
+        m.forward_head(torch.zeros(1, 24, 128))
+
+
 def test_pos_embed_resize_on_load():
     import uit_mobile_b200 as U
     sd = H.make_state_dict("uit_xxxs", grid_t=6)

@@ -364,6 +364,16 @@ class UITBase(nn.Module):
             self._last_workspace = ws
         return probs
 
+    def forward_features(self, x):
+        """Reference: uit.py:379-396 (tokens after the final LayerNorm).  The B200 path never materialises them: BatchNorm,
+        patch embedding, all blocks, the final norm and the token mean are one fused kernel (see ``encode``)."""
+        raise NotImplementedError("forward_features is fused into UITBase.encode() on the B200 path (no per-stage tensors); "
+                                  "use model(x) / model.encode(db, max_pow)")
+
+    def forward_head(self, x):
+        """Reference: uit.py:398-412.  Fused into ``encode`` (head LayerNorm + Linear + sigmoid + crop reduction)."""
+        raise NotImplementedError("forward_head is fused into UITBase.encode() on the B200 path; use model(x)")
+
     def tile_clips(self, T: int) -> int:
         """Clips per 128-row encoder tile for T frames: chunk / shard boundaries that are multiples of this (in clips)
         reproduce a single launch bit for bit."""
@@ -381,6 +391,8 @@ class UITBase(nn.Module):
                                       "(training branches of uit.py:453-459 are out of scope)")
         if self.eval_avg not in ('mean', 'max'):
             raise ValueError(f'Unknown Eval average function ({self.eval_avg})')
+        if x.dim() == 2 and x.shape[0] == 0:
+            return torch.empty((0, self.outputdim), dtype=torch.float32, device=x.device)
         db, max_pow = self.front_end.logmel_unclamped(x)
         if self.process_group is not None:
             # Q2: the top-dB cutoff is batch-global; with the batch sharded over GPUs the scope is the global batch.
