@@ -113,3 +113,15 @@ def test_bf16_persistent_many_tiles_per_cta_equals_small_batches():
     full = m.encode(db, mp)
     part = torch.cat([m.encode(db[i:i + 5].contiguous(), mp) for i in range(0, 50, 5)])
     assert torch.equal(full[:50], part)
+
+
+@pytest.mark.parametrize("L", [2400, 4000, 8160, 14336, 16000, 16160, 16384, 33000])
+def test_bf16_vs_fp32_device_paths_over_shapes(L):
+    """Shape sweep on the device: the tensor-core path against the exact fp32 CUDA path for every token count (4..24 tokens,
+    1..3 crops) and batch sizes that leave ragged tiles.  Covers the CUDA-core attention fallback (tokens != 24) too."""
+    mb, mf = _model("uit_xxs", "init", "bf16"), _model("uit_xxs", "init", "fp32")
+    for B in (1, 4, 6, 37):
+        x = torch.from_numpy(H.noise_clips(B, L, seed=100 + B)).to(DEV)
+        yb, yf = mb(x), mf(x)
+        assert yb.shape == yf.shape == (B, 537) and torch.isfinite(yb).all()
+        assert (yb - yf).abs().max().item() <= TOL["init"], (L, B)
