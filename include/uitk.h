@@ -134,6 +134,12 @@ UITK_API size_t uitk_encoder_tokens_offset(const uitk_encoder_cfg* cfg, int64_t 
  * (before the final LayerNorm) to the start of the workspace, like the fp32 path does. */
 UITK_API void uitk_debug_taps(int enable);
 
+/* Profiling only: when the library is built with -DUITK_TRACE (UITK_TRACE=1 python -m uit_mobile_b200.build), CTA 0 of
+ * the tensor-core encoder stamps (stage id << 44 | SM clock) at every stage boundary; `which` 0 = compute thread 0,
+ * 1 = the MMA-issuer thread.  Copies the first n (<= 4096) stamps of the last launch to host_out (synchronises).
+ * Returns UITK_EINVAL in a normal build. */
+UITK_API int uitk_debug_read_trace(long long* host_out, int which, int n);
+
 /* Tests only: one 128 x N x K tcgen05 GEMM through the library's descriptor / TMEM / bulk-copy plumbing.
  * d_B_packed is bf16 in the K-major core-matrix layout documented in csrc/tc_ptx.cuh; C (+)= A B^T in fp32. */
 UITK_API int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K,

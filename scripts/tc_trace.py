@@ -1,0 +1,78 @@
+"""Stage timeline of the tensor-core encoder (needs a -DUITK_TRACE build: UITK_TRACE=1 python -m uit_mobile_b200.build --force).
+
+Prints, for CTA 0, the mean cycles between consecutive stage stamps of compute thread 0 over all blocks of each tile, and
+the same for the MMA-issuer thread.  Output also lands in gpurun_out/tc_trace.txt.
+"""
+import os
+import sys
+from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import uit_mobile_b200 as U
+from uit_mobile_b200 import _native as N
+
+NAMES = {1: "tile start", 2: "patch gather+signal", 3: "patch MMA wait", 10: "pos add / block start (param wait)",
+         11: "LN1+signal", 12: "qkv MMA wait", 13: "qkv epilogue+signal", 14: "S MMA wait", 15: "softmax+P+signal",
+         16: "PV MMA wait", 17: "O read(+signal)", 18: "A_o signal", 19: "proj MMA wait", 20: "LN2+signal",
+         21: "fc1/H wait", 22: "relu epilogue+signal", 23: "final fc2 waits", 30: "final LN + pool"}
+INAMES = {1: "wait_ready", 2: "weights FULL wait", 3: "MMAs issued+commit"}
+
+
+def decode(buf):
+    ids = (buf >> 44).astype(np.int64)
+    clk = (buf & ((1 << 44) - 1)).astype(np.int64)
+    n = int(np.argmax(ids == 0)) if (ids == 0).any() else len(ids)
+    return ids[:n], clk[:n]
+
+
+def main():
+    batch = int(os.environ.get("TRACE_BATCH", 4096))
+    arch = os.environ.get("TRACE_ARCH", "uit_xs")
+    lib = N.lib()
+    torch.manual_seed(0)
+    model = getattr(U.models, arch)(outputdim=537, target_length=102).to("cuda:0").eval()
+    x = (0.1 * torch.randn(batch, 16000, device="cuda:0")).clamp_(-1, 1)
+    with torch.no_grad():
+        for _ in range(3):
+            model(x)
+    torch.cuda.synchronize()
+    out = []
+    for which, names in ((0, NAMES), (1, INAMES)):
+        buf = np.zeros(4096, dtype=np.int64)
+        N.check(lib.uitk_debug_read_trace(buf.ctypes.data, which, 4096), "read_trace")
+        ids, clk = decode(buf)
+        out.append(f"== {'compute thread 0' if which == 0 else 'MMA issuer'}: {len(ids)} stamps, total {clk[-1] - clk[0]} cycles")
+        d = np.diff(clk)
+        agg = defaultdict(list)
+        if which == 0:
+            # key = (previous id, id, occurrence index within the block for repeated ids)
+            occ = defaultdict(int)
+            for i in range(1, len(ids)):
+                if ids[i] == 10:
+                    occ.clear()
+                k = (int(ids[i - 1]), int(ids[i]))
+                occ[k] += 1
+                agg[(k, occ[k])].append(int(d[i - 1]))
+            block_total = [int(clk[j] - clk[i]) for i, j in zip(np.where(ids == 10)[0][:-1], np.where(ids == 10)[0][1:]) if j - i < 40]
+            out.append(f"   cycles per block (stamp 10 -> next 10): mean {np.mean(block_total):.0f}  min {np.min(block_total)}  max {np.max(block_total)}")
+            order = sorted(agg.keys(), key=lambda k: min(i for i in range(1, len(ids)) if (int(ids[i - 1]), int(ids[i])) == k[0]) * 100 + k[1])
+            for k in order:
+                v = agg[k]
+                out.append(f"   {names.get(k[0][0], k[0][0])!s:>36} -> {names.get(k[0][1], k[0][1])!s:<36} #{k[1]:<2d} n={len(v):3d} mean {np.mean(v):8.0f}  min {np.min(v):6d}  max {np.max(v):6d}")
+        else:
+            for i in range(1, len(ids)):
+                agg[(int(ids[i - 1]), int(ids[i]))].append(int(d[i - 1]))
+            for k, v in sorted(agg.items()):
+                out.append(f"   {names.get(k[0], k[0])!s:>24} -> {names.get(k[1], k[1])!s:<24} n={len(v):4d} mean {np.mean(v):8.0f}  min {np.min(v):6d}  max {np.max(v):6d}  sum {np.sum(v):9d}")
+    txt = "\n".join(out)
+    print(txt)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/tc_trace.txt", "w") as f:
+        f.write(txt + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,7 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uitk_encoder_tokens_offset": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
     "uitk_debug_taps": (None, [C.c_int]),
+    "uitk_debug_read_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "uitk_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 

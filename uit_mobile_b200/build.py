@@ -36,6 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("UITK_TRACE"):        # in-kernel stage timeline of the tensor-core encoder (profiling builds only)
+        flags.append("-DUITK_TRACE")
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []

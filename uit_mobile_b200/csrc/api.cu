@@ -111,6 +111,11 @@ int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const 
 
 void uitk_debug_taps(int enable) { g_debug_taps = enable; }
 
+int uitk_debug_read_trace(long long* host_out, int which, int n) {
+  UITK_REQUIRE(host_out, UITK_EINVAL, "null pointer");
+  return read_encoder_trace(host_out, which, n);
+}
+
 int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K, void* stream) {
   UITK_REQUIRE(d_A && d_B_packed && d_C, UITK_EINVAL, "null pointer");
   int rc = check_arch();

@@ -17,6 +17,8 @@
 //   * attention (2 heads x 24 x 24 x 16 per clip) stays on the CUDA cores, one thread per (row, head), fp32 softmax.
 // LayerNorm, softmax, residual and all accumulation are fp32; only GEMM operands are rounded to bf16.
 // Reference semantics: models/uit.py:379-396 (features), 89-122 (attention), 181-248 (MLP, block).
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 #include "uitk_common.cuh"
 
@@ -69,6 +71,15 @@ struct TcParams {
   float* dbg_x;    // optional [RR*tokens][128]: residual stream after the last block (pre final LN)
   int tc_attn;     // 1: attention GEMMs on tcgen05 (needs tokens == 24); 0: CUDA-core attention
 };
+
+// Optional in-kernel timeline (build with -DUITK_TRACE): thread 0 of CTA 0 and its MMA-issuer thread stamp
+// (id << 44 | clock) at every stage boundary; read back with uitk_debug_read_trace.  Compiled out by default.
+#ifdef UITK_TRACE
+__device__ long long g_trace[2][4096];
+#define TR(buf, id) do { if (trace_on && tr_n < 4096) g_trace[buf][tr_n++] = ((long long)(id) << 44) | (clock64() & ((1ll << 44) - 1)); } while (0)
+#else
+#define TR(buf, id) do {} while (0)
+#endif
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // wait executed by every thread of a warp: re-converge before the .sync.aligned tcgen05 instructions that follow
@@ -136,13 +147,27 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
   }
 }
 
+// relu(v + b) for 8 consecutive hidden columns -> one 16-byte bf16 chunk
+__device__ __forceinline__ uint4 bias_relu_pack8(const float* v, const float* b) {
+  const float4 ba = *reinterpret_cast<const float4*>(b), bc = *reinterpret_cast<const float4*>(b + 4);
+  const float2 t0 = add2(make_float2(v[0], v[1]), make_float2(ba.x, ba.y));
+  const float2 t1 = add2(make_float2(v[2], v[3]), make_float2(ba.z, ba.w));
+  const float2 t2 = add2(make_float2(v[4], v[5]), make_float2(bc.x, bc.y));
+  const float2 t3 = add2(make_float2(v[6], v[7]), make_float2(bc.z, bc.w));
+  uint4 o;
+  o.x = pack2_relu_bf16(t0.x, t0.y); o.y = pack2_relu_bf16(t1.x, t1.y);
+  o.z = pack2_relu_bf16(t2.x, t2.y); o.w = pack2_relu_bf16(t3.x, t3.y);
+  return o;
+}
+
 __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
   float* part = reinterpret_cast<float*>(smem + OFF_PART);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches stay uniform
 
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_READY || i == B_READY + 1) ? kCompute / 32 : 1);   // one arrive per compute warp
@@ -159,12 +184,16 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 
   if (warp == 8) {
     // =================================== weight producer =======================================
-    if (lane == 0) {
+    // warp-uniform code, one elected lane issues the bulk copies (see the MMA issuer below for why)
+    {
       uint32_t slot = 0, phase = 0, ps = 0, pphase = 0;
       auto ring_load = [&](const unsigned char* src, uint32_t bytes) {
         mbar_wait(&bars[B_EMPTYW + slot], phase ^ 1);
-        mbar_arrive_expect_tx(&bars[B_FULLW + slot], bytes);
-        bulk_g2s(smem + OFF_RING + slot * kSlot, src, bytes, &bars[B_FULLW + slot]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars[B_FULLW + slot], bytes);
+          bulk_g2s(smem + OFF_RING + slot * kSlot, src, bytes, &bars[B_FULLW + slot]);
+        }
+        __syncwarp();
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -172,8 +201,11 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         for (int blk = 0; blk < p.depth; ++blk) {
           const unsigned char* wb = p.wts + kPatchBytes + (size_t)blk * kBlockBytes;
           mbar_wait(&bars[B_EMPTYP + ps], pphase ^ 1);
-          mbar_arrive_expect_tx(&bars[B_FULLP + ps], kParamBytes);
-          bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars[B_FULLP + ps], kParamBytes);
+            bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
+          }
+          __syncwarp();
           if (++ps == 2) { ps = 0; pphase ^= 1; }
           wb += kParamBytes;
           ring_load(wb, kQkvHalfBytes); wb += kQkvHalfBytes;
@@ -185,69 +217,100 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     }
   } else if (warp == 9) {
     // =================================== MMA issuer =======================================
-    // One thread issues every tcgen05.mma of the CTA.  It waits for (a) the "operand ready" signal of the 256 compute
-    // threads (alternating mbarriers, count 256) and (b) the weight chunk in the ring; the compute warps never block on
-    // weights, only on the completion barriers (ACC / X / FC1 / H) of the MMAs whose results they read.
-    if (lane == 0) {
+    // One warp issues every tcgen05.mma of the CTA.  ALL 32 lanes run this (warp-uniform) code and one elected lane
+    // executes the tcgen05 instructions: the descriptors then live in uniform registers and the UTCHMMA instructions go
+    // out back to back.  (Issuing from inside an `if (lane == 0)` region makes the compiler wrap every MMA in an
+    // R2UR + ELECT waterfall loop, ~75-135 cycles per instruction: measured, scripts/microbench/tc_micro.cu.)
+    // It waits for (a) the "operand ready" signal of the 256 compute threads (alternating mbarriers) and (b) the weight
+    // chunk in the ring; the compute warps never block on weights, only on the completion barriers (ACC / X / FC1 / H).
+    {
       const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
+      const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sVT = smem_u32(smem + OFF_VT), sP = smem_u32(smem + OFF_P);
       constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
       constexpr uint32_t ID16 = make_idesc_bf16(128, 16);
       const bool tc_attn = p.tc_attn != 0;
       uint32_t cslot = 0, cphase = 0, sig = 0;
+#ifdef UITK_TRACE
+      const bool trace_on = blockIdx.x == 0 && lane == 0;
+      int tr_n = 0;
+#endif
       auto wait_ready = [&]() {
         mbar_wait(&bars[B_READY + (sig & 1)], (sig >> 1) & 1);
         ++sig;
         tc_fence_after();
+        TR(1, 1);
       };
-      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, int ksteps, bool accum_first) {
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+      };
+      // KSTEPS MMAs (K = 16 each) of A[128 x 16*KSTEPS] (k-groups 2048 B apart) with the B chunk in the current ring slot
+      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, auto ksteps_c, bool accum_first) {
+        constexpr int KSTEPS = decltype(ksteps_c)::value;
         mbar_wait(&bars[B_FULLW + cslot], cphase);
         tc_fence_after();
+        TR(1, 2);
         const uint32_t b_base = sRing + cslot * kSlot;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
-                    (accum_first || ks > 0) ? 1u : 0u);
-        umma_commit(&bars[B_EMPTYW + cslot]);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
+                      (accum_first || ks > 0) ? 1u : 0u);
+          umma_commit(&bars[B_EMPTYW + cslot]);
+        }
+        __syncwarp();
+        TR(1, 3);
         if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
       };
+      using K2 = std::integral_constant<int, 2>;
+      using K4 = std::integral_constant<int, 4>;
+      using K8 = std::integral_constant<int, 8>;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         wait_ready();                                                         // patch operand gathered
-        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, 4, c > 0);
-        umma_commit(&bars[B_ACC]);
+        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, K4{}, c > 0);
+        commit(&bars[B_ACC]);
         for (int blk = 0; blk < p.depth; ++blk) {
           wait_ready();                                                       // LN1 output in A
-          mma_from_ring(tmem + 128, sA, ID96, 1536, 4, false);
-          mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, 4, true);
-          umma_commit(&bars[B_ACC]);
+          mma_from_ring(tmem + 128, sA, ID96, 1536, K4{}, false);
+          mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, K4{}, true);
+          commit(&bars[B_ACC]);
           if (tc_attn) {                                                      // attention GEMMs (no weights involved)
             for (int h = 0; h < 2; ++h) {
               wait_ready();                                                   // Q/K/V^T operands written (h=0) / ACC drained (h=1)
-              umma_bf16(tmem + 128, make_smem_desc(smem_u32(smem + OFF_Q) + h * 4096, 2048, 128),
-                        make_smem_desc(smem_u32(smem + OFF_K) + h * 4096, 2048, 128), ID128, 0u);          // S_h = Q_h K_h^T
-              umma_commit(&bars[B_ACC]);
+              if (elect_one()) {
+                umma_bf16(tmem + 128, make_smem_desc(sQ + h * 4096, 2048, 128), make_smem_desc(sK + h * 4096, 2048, 128), ID128, 0u);   // S_h = Q_h K_h^T
+                umma_commit(&bars[B_ACC]);
+              }
+              __syncwarp();
               wait_ready();                                                   // P_h written, S_h consumed
-              for (int ks = 0; ks < 8; ++ks)                                  // O_h = P_h V_h  (N = 16, K = 128)
-                umma_bf16(tmem + 128, make_smem_desc(smem_u32(smem + OFF_P) + ks * 4096, 2048, 128),
-                          make_smem_desc(smem_u32(smem + OFF_VT) + h * 4096 + ks * 512, 256, 128), ID16, ks > 0 ? 1u : 0u);
-              umma_commit(&bars[B_ACC]);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)                                // O_h = P_h V_h  (N = 16, K = 128)
+                  umma_bf16(tmem + 128, make_smem_desc(sP + ks * 4096, 2048, 128), make_smem_desc(sVT + h * 4096 + ks * 512, 256, 128), ID16,
+                            ks > 0 ? 1u : 0u);
+                umma_commit(&bars[B_ACC]);
+              }
+              __syncwarp();
             }
           }
           wait_ready();                                                       // attention output in A_o
-          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, 2, true);         // x += o Wproj^T (bias deferred into cb2)
-          umma_commit(&bars[B_X]);
+          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, K2{}, true);      // x += o Wproj^T (bias deferred into cb2)
+          commit(&bars[B_X]);
           wait_ready();                                                       // LN2 output in A
-          for (int c = 0; c < 2; ++c) {
-            mma_from_ring(tmem + 128 + c * 64, sA, ID64, 1024, 8, false);
-            umma_commit(&bars[B_FC1 + c]);
-          }
-          for (int c = 0; c < 6; ++c) {
-            const int bsel = c & 1;
-            wait_ready();                                                     // H[bsel] written, accumulator bsel drained
-            mma_from_ring(tmem, sH + bsel * 16384, ID128, 2048, 4, true);     // fc2[c]: x += H_c W2_c^T
-            umma_commit(&bars[B_H + bsel]);
-            if (c + 2 < 6) {                                                  // fc1[c+2] into the accumulator just drained
-              mma_from_ring(tmem + 128 + bsel * 64, sA, ID64, 1024, 8, false);
-              umma_commit(&bars[B_FC1 + bsel]);
+          mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);            // fc1[0]: hidden 0..127, K half 0
+          mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true);     //                        K half 1
+          commit(&bars[B_FC1]);
+          for (int c = 0; c < 3; ++c) {
+            wait_ready();                                                     // accumulator drained into registers
+            if (c < 2) {                                                      // fc1[c+1] runs while the ReLU epilogue of chunk c does
+              mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);
+              mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true);
+              commit(&bars[B_FC1]);
             }
+            wait_ready();                                                     // H (chunk c) written
+            mma_from_ring(tmem, sH, ID128, 2048, K4{}, true);                 // fc2[c]: x += H_c W2_c^T  (K = 128 hidden)
+            mma_from_ring(tmem, sH + 16384, ID128, 2048, K4{}, true);
+            commit(&bars[B_H]);
           }
         }
       }
@@ -259,13 +322,24 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
     const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
     uint32_t ps = 0, pphase = 0;          // param slot
-    uint32_t ph_acc = 0, ph_x = 0, ph_fc1[2] = {0, 0}, ph_h[2] = {0, 0};
+    uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0;
     uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
+#ifdef UITK_TRACE
+    const bool trace_on = blockIdx.x == 0 && tid == 0;
+    int tr_n = 0;
+#endif
     // operand written by this thread is visible to the async proxy, its TMEM reads are done: tell the MMA issuer
     // (every thread fences its own writes; __syncwarp orders the warp; ONE lane arrives -> 8 arrivals per signal instead
     // of 256 serialized shared-memory atomics)
     auto signal_ready = [&]() {
       fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_READY + (sig & 1)]);
+      ++sig;
+    };
+    // same signal stream, but nothing was written to shared memory: this thread's TMEM reads are done
+    auto signal_drained = [&]() {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_READY + (sig & 1)]);
@@ -279,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       const int rr0 = tile * p.G;
       const int g_cnt = min(p.G, p.RR - rr0);
       const int rows_valid = g_cnt * tokens;
+      TR(0, 1);
 
       // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A[128 x 256] over A|H ----------------
       for (int i = tid; i < (128 - rows_valid) * 32; i += kCompute) {      // zero the padding rows
@@ -318,8 +393,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         }
       }
       signal_ready();
+      TR(0, 2);
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      TR(0, 3);
       {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383), written back to TMEM once
         const int tok = r % tokens, f = tok / t_n, tau = tok - f * t_n;
 #pragma unroll
@@ -347,13 +424,16 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       for (int blk = 0; blk < p.depth; ++blk) {
         mbar_wait_all(&bars[B_FULLP + ps], pphase);
         const float* prm = reinterpret_cast<const float*>(smem + OFF_PARAM + ps * kParamBytes);
+        TR(0, 10);
         const float *cb1 = prm + 256, *qkv_b = prm + 384, *cb2 = prm + 768, *b1 = prm + 896;   // LN affine is folded into W/b
 
         // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
         ln_to_operand(tx, hsel, r, cb1, 1e-6f, part, smem + OFF_A);
         signal_ready();
+        TR(0, 11);
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
+        TR(0, 12);
         if (p.tc_attn) {
           // ---------- tensor-core attention: S_h = Q_h K_h^T and O_h = P_h V_h on tcgen05, softmax straight from TMEM ----------
           const bool valid = r < rows_valid;
@@ -395,11 +475,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             }
           }
           signal_ready();
+          TR(0, 13);
           constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // softmax(0.125 * s) through exp2
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // S_h in ACC
             tc_fence_after();
+            TR(0, 14);
             // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp straddle two clips: load the
             // key window of each of the two clips in turn and let every lane keep the one that belongs to its row
             float sv[16];
@@ -452,13 +534,16 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
               }
             }
             signal_ready();                                               // P_h complete, S_h consumed
+            TR(0, 15);
             mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // O_h in ACC columns 0..15
             tc_fence_after();
+            TR(0, 16);
             float o[8];
             tmem_ld8(tacc + hsel * 8, o);
             tmem_ld_wait();
             *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + hsel) * 2048 + r * 16) = pack8_bf16(o);
             if (h == 0) signal_ready();                                   // ACC drained: S_1 may overwrite it
+            TR(0, 17);
           }
         } else {
         {   // qkv (+bias) -> fp32 scratch [128][100]
@@ -548,43 +633,40 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         }
         }
         signal_ready();
+        TR(0, 18);
         mbar_wait_all(&bars[B_X], ph_x); ph_x ^= 1;
         tc_fence_after();
+        TR(0, 19);
 
         // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
         ln_to_operand(tx, hsel, r, cb2, 1e-6f, part + 512, smem + OFF_A);
         signal_ready();
+        TR(0, 20);
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-          const int bsel = c & 1;
-          mbar_wait_all(&bars[B_FC1 + bsel], ph_fc1[bsel]); ph_fc1[bsel] ^= 1;
-          if (c >= 2) { mbar_wait_all(&bars[B_H + bsel], ph_h[bsel]); ph_h[bsel] ^= 1; }   // fc2[c-2] finished reading H[bsel]
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait_all(&bars[B_FC1], ph_fc1); ph_fc1 ^= 1;
           tc_fence_after();
-          unsigned char* H = smem + OFF_H + bsel * 16384;
-          {
-            float v[32];
-            tmem_ld32(tacc + bsel * 64 + hsel * 32, v);
-            tmem_ld_wait();
+          TR(0, 21);
+          float v0[32], v1[32];                                           // this thread's 64 hidden columns of the chunk
+          tmem_ld32(tacc + hsel * 64, v0);
+          tmem_ld32(tacc + hsel * 64 + 32, v1);
+          tmem_ld_wait();
+          signal_drained();                                               // fc1[c+1] may overwrite the accumulator
+          TR(0, 24);
+          if (c >= 1) { mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1; }     // fc2[c-1] finished reading H
+          unsigned char* H = smem + OFF_H + hsel * 16384 + r * 16;
+          const float* bb = b1 + c * 128 + hsel * 64;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              float y[8];
-              const float* bb = b1 + c * 64 + hsel * 32 + cc * 8;
-              const float4 ba = *reinterpret_cast<const float4*>(bb), bc = *reinterpret_cast<const float4*>(bb + 4);
-              const float2 t0 = add2(make_float2(v[cc * 8 + 0], v[cc * 8 + 1]), make_float2(ba.x, ba.y));
-              const float2 t1 = add2(make_float2(v[cc * 8 + 2], v[cc * 8 + 3]), make_float2(ba.z, ba.w));
-              const float2 t2 = add2(make_float2(v[cc * 8 + 4], v[cc * 8 + 5]), make_float2(bc.x, bc.y));
-              const float2 t3 = add2(make_float2(v[cc * 8 + 6], v[cc * 8 + 7]), make_float2(bc.z, bc.w));
-              y[0] = fmaxf(t0.x, 0.f); y[1] = fmaxf(t0.y, 0.f); y[2] = fmaxf(t1.x, 0.f); y[3] = fmaxf(t1.y, 0.f);
-              y[4] = fmaxf(t2.x, 0.f); y[5] = fmaxf(t2.y, 0.f); y[6] = fmaxf(t3.x, 0.f); y[7] = fmaxf(t3.y, 0.f);
-              *reinterpret_cast<uint4*>(H + (hsel * 4 + cc) * 2048 + r * 16) = pack8_bf16(y);
-            }
-          }
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = bias_relu_pack8(v0 + cc * 8, bb + cc * 8);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + (4 + cc) * 2048) = bias_relu_pack8(v1 + cc * 8, bb + 32 + cc * 8);
           signal_ready();
+          TR(0, 22);
         }
-        // block end: fc2[4] (H0) and fc2[5] (H1) complete => x is final for this block, params/H/A reusable
-        mbar_wait_all(&bars[B_H + 0], ph_h[0]); ph_h[0] ^= 1;
-        mbar_wait_all(&bars[B_H + 1], ph_h[1]); ph_h[1] ^= 1;
+        // block end: fc2[2] complete => x is final for this block, params/H/A reusable
+        mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1;
         tc_fence_after();
+        TR(0, 23);
         if (tid == 0) mbar_arrive(&bars[B_EMPTYP + ps]);
         __syncwarp();
         if (++ps == 2) { ps = 0; pphase ^= 1; }
@@ -628,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           p.pooled[(size_t)(rr0 + g) * 128 + col] = acc * invn;
         }
         bar_compute();     // Y (aliases A|H) is free again before the next tile's gather
+        TR(0, 30);
       }
     }
   }
@@ -643,6 +726,18 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
+
+int read_encoder_trace(long long* host_out, int which, int n) {
+#ifdef UITK_TRACE
+  if (which < 0 || which > 1 || n < 0 || n > 4096) return UITK_EINVAL;
+  UITK_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(long long), (size_t)which * 4096 * sizeof(long long)));
+  return UITK_OK;
+#else
+  (void)host_out; (void)which; (void)n;
+  set_error("libuitk was built without -DUITK_TRACE");
+  return UITK_EINVAL;
+#endif
+}
 
 size_t encoder_tc_bf16_section_bytes(int depth) { return (size_t)kPatchBytes + (size_t)depth * kBlockBytes; }
 size_t encoder_tc_block_bytes() { return kBlockBytes; }

@@ -261,9 +261,14 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
       pack_kmajor(w, wq.data(), 128, 0, 96, 0, 64); w += 96 * 64;               // Wqkv' [96][128], K half 0
       pack_kmajor(w, wq.data(), 128, 0, 96, 64, 64); w += 96 * 64;              // Wqkv', K half 1
       pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // Wproj [128][32]
-      auto w1 = [&](int c) { pack_kmajor(w, w1f.data(), 128, c * 64, 64, 0, 128); w += 64 * 128; };   // fc1' rows 64c..
-      auto w2 = [&](int c) { pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64; };        // fc2 K slice 64c..
-      w1(0); w1(1); w2(0); w1(2); w2(1); w1(3); w2(2); w1(4); w2(3); w1(5); w2(4); w2(5);
+      // MLP in 3 chunks of 128 hidden units; every 16 KB ring slot is one [128 x 64] K-major tile (4 MMA k-steps)
+      auto w1 = [&](int c) {                                                     // fc1' rows 128c.., K halves
+        for (int kh = 0; kh < 2; ++kh) { pack_kmajor(w, w1f.data(), 128, c * 128, 128, kh * 64, 64); w += 128 * 64; }
+      };
+      auto w2 = [&](int c) {                                                     // fc2 K slices 128c + 64hh ..
+        for (int hh = 0; hh < 2; ++hh) { pack_kmajor(w, b[10], 384, 0, 128, c * 128 + hh * 64, 64); w += 128 * 64; }
+      };
+      w1(0); w1(1); w2(0); w1(2); w2(1); w2(2);
     }
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
   }

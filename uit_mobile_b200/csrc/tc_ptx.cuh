@@ -44,6 +44,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully converged) warp: the issuing lane of warp-uniform tcgen05 / bulk-copy code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- async proxy ----------------------------------------------------------------------------------------------------
 // Generic-proxy writes to shared memory (st.shared) must be fenced before the async proxy (UMMA / TMA) reads them.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -176,6 +183,13 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
+}
+
+// max(x, 0) rounded to bf16 (nearest even) for two values in ONE instruction (cvt.rn.relu.bf16x2.f32): lo in bits 0..15
+__device__ __forceinline__ uint32_t pack2_relu_bf16(float lo, float hi) {
+  uint32_t o;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
+  return o;
 }
 
 // pack 8 fp32 -> 8 bf16 (round to nearest even) as one 16-byte chunk
