@@ -145,6 +145,11 @@ UITK_API int uitk_debug_read_trace(long long* host_out, int which, int n);
 UITK_API int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K,
                                 void* stream);
 
+/* Same GEMM with the A operand staged in TENSOR MEMORY (tcgen05.mma with a TMEM A operand, as the encoder's P V
+ * attention product uses it): pins the packed-bf16 TMEM operand layout. */
+UITK_API int uitk_selftest_umma_ts(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,25 @@ def test_umma_selftest(N, K, init):
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("N,K,init", [(16, 128, False), (128, 128, False), (64, 64, True), (16, 16, False)])
+def test_umma_selftest_a_in_tmem(N, K, init):
+    """tcgen05.mma with the A operand in tensor memory (the layout the encoder's P V product relies on)."""
+    from uit_mobile_b200 import _native as N_
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    a = torch.randn(128, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    c0 = torch.randn(128, N, generator=g) if init else None
+    ref = a.to(torch.bfloat16).double() @ b.to(torch.bfloat16).double().T + (c0.double() if init else 0)
+    a_d, bp_d = a.to(DEV), pack_kmajor(b).to(DEV)
+    c0_d = c0.to(DEV) if init else None
+    out = torch.full((128, N), float("nan"), device=DEV)
+    N_.check(N_.lib().uitk_selftest_umma_ts(a_d.data_ptr(), bp_d.data_ptr(), c0_d.data_ptr() if init else None, out.data_ptr(), N, K,
+                                            torch.cuda.current_stream().cuda_stream), "uitk_selftest_umma_ts")
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
 def _model(arch, kind, precision, depth=None, **kw):
     import uit_mobile_b200 as U
     sd = H.make_state_dict(arch, kind)

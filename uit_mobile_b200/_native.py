@@ -48,6 +48,7 @@ SIGNATURES = {
     "uitk_debug_taps": (None, [C.c_int]),
     "uitk_debug_read_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "uitk_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "uitk_selftest_umma_ts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

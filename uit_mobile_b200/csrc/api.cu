@@ -120,7 +120,14 @@ int uitk_selftest_umma(const float* d_A, const void* d_B_packed, const float* d_
   UITK_REQUIRE(d_A && d_B_packed && d_C, UITK_EINVAL, "null pointer");
   int rc = check_arch();
   if (rc != UITK_OK) return rc;
-  return run_umma_selftest(d_A, d_B_packed, d_C_init, d_C, N, K, reinterpret_cast<cudaStream_t>(stream));
+  return run_umma_selftest(d_A, d_B_packed, d_C_init, d_C, N, K, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int uitk_selftest_umma_ts(const float* d_A, const void* d_B_packed, const float* d_C_init, float* d_C, int N, int K, void* stream) {
+  UITK_REQUIRE(d_A && d_B_packed && d_C, UITK_EINVAL, "null pointer");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return run_umma_selftest(d_A, d_B_packed, d_C_init, d_C, N, K, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

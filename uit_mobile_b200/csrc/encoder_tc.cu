@@ -30,14 +30,16 @@ using namespace tc;
 
 constexpr int kThreads = 320;          // 8 compute warps + TMA producer warp + MMA issuer warp
 constexpr int kCompute = 256;
-constexpr uint32_t kSlot = 16384;
+constexpr uint32_t kTile = 16384;                     // one [128 x 64] bf16 K-major weight tile = 4 MMA k-steps
+constexpr uint32_t kBiasTile = 128 * 16;              // [128 x 8] bf16 bias tile (pack.cu: pack_bias_tile)
+constexpr uint32_t kSlot = kTile + kBiasTile;         // ring slot: a weight tile and, for some, the bias tile behind it
 constexpr int kSlots = 2;
-constexpr uint32_t kParamFloats = 1280;               // ln1_w ln1_b cb1 qkv_b(128) ln2_w ln2_b cb2 b1(384)
-constexpr uint32_t kParamBytes = kParamFloats * 4;    // 5120
 constexpr uint32_t kQkvHalfBytes = 96 * 64 * 2;       // Wqkv, one K half: 12288
+constexpr uint32_t kQkvBiasBytes = 96 * 16;           // 1536
 constexpr uint32_t kProjBytes = 128 * 32 * 2;         // 8192
-constexpr uint32_t kBlockBytes = kParamBytes + 2 * kQkvHalfBytes + kProjBytes + 12 * kSlot;   // 234496
-constexpr uint32_t kPatchBytes = 4 * kSlot;           // 4 K-quarters of the patch weight
+// per block: [Wqkv k0 | bqkv] [Wqkv k1] [Wproj | bproj]  3 x ([W1 k0] [W1 k1 | b1])  3 x ([W2 h0] [W2 h1]) (+ b2 after the first)
+constexpr uint32_t kBlockBytes = 2 * kQkvHalfBytes + kQkvBiasBytes + kProjBytes + kBiasTile + 3 * (2 * kTile + kBiasTile) + 6 * kTile + kBiasTile;
+constexpr uint32_t kPatchBytes = 4 * kTile;           // 4 K-quarters of the patch weight
 
 // shared memory map (bytes); one CTA uses 108.3 KB so that two fit on an SM
 constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output) | patch k 0..127 | attention scratch
@@ -47,23 +49,31 @@ constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 + 16 B per
 // tensor-core attention operands (tokens == 24), all inside A|H which are idle between the qkv and proj GEMMs
 constexpr uint32_t OFF_Q = OFF_A + 8192;           // Q_h  [128 x 16] bf16 K-major, head h at + h*4096
 constexpr uint32_t OFF_K = OFF_A + 16384;          // K_h  [128 x 16] (B operand: N = key row)
-constexpr uint32_t OFF_VT = OFF_A + 24576;         // V_h^T [16 x 128] (B operand: N = d, K = key row; k-group stride 256 B)
-constexpr uint32_t OFF_P = OFF_H;                  // P_h  [128 x 128] bf16 K-major (block diagonal, zeros elsewhere), 32 KB
+// V_h^T [16 x 128] (B operand: N = d, K = key row).  k-groups are 272 B apart (LBO is free in the descriptor): the 4 key
+// groups a warp's 2-byte transposing stores hit then fall into distinct banks.  Head h at + h * kVtHead.
+constexpr uint32_t OFF_VT = OFF_H;
+constexpr uint32_t kVtLbo = 272, kVtHead = 16 * kVtLbo;
+// P_h (softmax probabilities, block diagonal) never touches shared memory: it is written to TENSOR MEMORY (accumulator
+// columns 0..63, packed bf16 pairs, over the dead S_h) and is the TMEM A operand of the P V product; O_h lands in
+// accumulator columns 64..79.
+constexpr uint32_t kColP = 0, kColO = 64;
 constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
-constexpr uint32_t OFF_PARAM = OFF_RING + kSlots * kSlot;   // 2 x 5120
-constexpr uint32_t OFF_PART = OFF_PARAM + 2 * kParamBytes;  // 2 x 512 floats
+// constant MMA operands: k-group of (1, 1, 1, 0, ..) rows = the A operand of every bias k-step, then 2 KB of zeros that
+// serve as the second k-group of both the ones operand and every bias tile (their LBO points here: it must lie ABOVE the ring)
+constexpr uint32_t OFF_CONST = OFF_RING + kSlots * kSlot;
+constexpr uint32_t OFF_PART = OFF_CONST + 4096;             // 2 x 512 floats
 constexpr uint32_t OFF_BAR = OFF_PART + 2 * 512 * 4;   // two alternating buffers of [2][128] float2 partial sums
 constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = 2, B_FULLP = 4, B_EMPTYP = 6, B_ACC = 8, B_X = 9, B_FC1 = 10, B_H = 12, B_READY = 14, B_COUNT = 16 };
+enum { B_FULLW = 0, B_EMPTYW = 2, B_ACC = 4, B_X = 5, B_FC1 = 6, B_H = 7, B_READY = 8, B_COUNT = 10 };
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
   const float* patch_b; const float* time_pos; const float* freq_pos;
   const float* bn_scale; const float* bn_shift;
-  const float* norm_w; const float* norm_b; const float* cb_final;
+  const float* norm_w; const float* norm_b;
   const float* db; const uint32_t* max_pow;
   int T, crops, tokens, t_n, target;
   int RR, G, num_tiles, depth;
@@ -88,11 +98,10 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 }
 
-// Row statistics of (x + cb) for this thread's row in ONE pass (sum and sum of squares; var = E[x^2] - mean^2 in fp32:
-// |mean| is O(std) for these activations, the cancellation costs < 1e-6 relative).  The two threads of a row
-// (hsel 0/1) each reduce 64 columns and exchange partial sums through `part` with a single barrier.
-__device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part, float& mean,
-                                          float& rstd) {
+// Row statistics of this thread's row of x in ONE pass (sum and sum of squares; var = E[x^2] - mean^2 in fp32: |mean| is
+// O(std) for these activations, the cancellation costs < 1e-6 relative).  The two threads of a row (hsel 0/1) each
+// reduce 64 columns and exchange partial sums through `part` with a single barrier.
+__device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, float eps, float* part, float& mean, float& rstd) {
   float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);     // packed fp32x2 accumulators (even, odd columns)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -100,13 +109,10 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const fl
     tmem_ld32(tx + hsel * 64 + j * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 c4 = *reinterpret_cast<const float4*>(cb + hsel * 64 + j * 32 + i);
-      const float2 xa = add2(make_float2(v[i], v[i + 1]), make_float2(c4.x, c4.y));
-      const float2 xb = add2(make_float2(v[i + 2], v[i + 3]), make_float2(c4.z, c4.w));
-      s2 = add2(s2, add2(xa, xb));
+    for (int i = 0; i < 32; i += 2) {
+      const float2 xa = make_float2(v[i], v[i + 1]);
+      s2 = add2(s2, xa);
       q2 = fma2(xa, xa, q2);
-      q2 = fma2(xb, xb, q2);
     }
   }
   const float s = s2.x + s2.y, ss = q2.x + q2.y;
@@ -121,10 +127,9 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, const fl
 // LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
 // Only the normalisation (x - mean) * rstd happens here: the affine part (gamma, beta) is folded into the weights
 // and bias of the Linear that consumes the operand when the weights are packed (W' = W diag(gamma), b' = b + W beta).
-__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, const float* cb, float eps, float* part,
-                                              unsigned char* dst) {
+__device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, float eps, float* part, unsigned char* dst) {
   float mean, rstd;
-  row_stats(tx, hsel, r, cb, eps, part, mean, rstd);
+  row_stats(tx, hsel, r, eps, part, mean, rstd);
   const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -134,29 +139,21 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float y[8];
-      const int k0 = hsel * 64 + j * 32 + c * 8;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cb + k0 + 4 * h);
-        const float2 ya = fma2(add2(make_float2(v[c * 8 + 4 * h], v[c * 8 + 4 * h + 1]), make_float2(c4.x, c4.y)), rs2, nm2);
-        const float2 yb = fma2(add2(make_float2(v[c * 8 + 4 * h + 2], v[c * 8 + 4 * h + 3]), make_float2(c4.z, c4.w)), rs2, nm2);
-        y[4 * h + 0] = ya.x; y[4 * h + 1] = ya.y; y[4 * h + 2] = yb.x; y[4 * h + 3] = yb.y;
+      for (int h = 0; h < 4; ++h) {
+        const float2 ya = fma2(make_float2(v[c * 8 + 2 * h], v[c * 8 + 2 * h + 1]), rs2, nm2);
+        y[2 * h] = ya.x; y[2 * h + 1] = ya.y;
       }
       *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
     }
   }
 }
 
-// relu(v + b) for 8 consecutive hidden columns -> one 16-byte bf16 chunk
-__device__ __forceinline__ uint4 bias_relu_pack8(const float* v, const float* b) {
-  const float4 ba = *reinterpret_cast<const float4*>(b), bc = *reinterpret_cast<const float4*>(b + 4);
-  const float2 t0 = add2(make_float2(v[0], v[1]), make_float2(ba.x, ba.y));
-  const float2 t1 = add2(make_float2(v[2], v[3]), make_float2(ba.z, ba.w));
-  const float2 t2 = add2(make_float2(v[4], v[5]), make_float2(bc.x, bc.y));
-  const float2 t3 = add2(make_float2(v[6], v[7]), make_float2(bc.z, bc.w));
+// relu(v) for 8 consecutive hidden columns -> one 16-byte bf16 chunk (the fc1 bias is already in the accumulator)
+__device__ __forceinline__ uint4 relu_pack8(const float* v) {
   uint4 o;
-  o.x = pack2_relu_bf16(t0.x, t0.y); o.y = pack2_relu_bf16(t1.x, t1.y);
-  o.z = pack2_relu_bf16(t2.x, t2.y); o.w = pack2_relu_bf16(t3.x, t3.y);
+  o.x = pack2_relu_bf16(v[0], v[1]); o.y = pack2_relu_bf16(v[2], v[3]);
+  o.z = pack2_relu_bf16(v[4], v[5]); o.w = pack2_relu_bf16(v[6], v[7]);
   return o;
 }
 
@@ -177,6 +174,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (tid < 256) {   // ones k-group (rows of 1, 1, 1, 0, 0, 0, 0, 0 in bf16) followed by the shared all-zero k-group
+    *reinterpret_cast<uint4*>(smem + OFF_CONST + tid * 16) = tid < 128 ? make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -186,32 +187,28 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     // =================================== weight producer =======================================
     // warp-uniform code, one elected lane issues the bulk copies (see the MMA issuer below for why)
     {
-      uint32_t slot = 0, phase = 0, ps = 0, pphase = 0;
-      auto ring_load = [&](const unsigned char* src, uint32_t bytes) {
+      uint32_t slot = 0, phase = 0;
+      auto ring_load = [&](const unsigned char*& src, uint32_t bytes) {
         mbar_wait(&bars[B_EMPTYW + slot], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars[B_FULLW + slot], bytes);
           bulk_g2s(smem + OFF_RING + slot * kSlot, src, bytes, &bars[B_FULLW + slot]);
         }
         __syncwarp();
+        src += bytes;
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < 4; ++c) ring_load(p.wts + (size_t)c * kSlot, kSlot);
-        for (int blk = 0; blk < p.depth; ++blk) {
-          const unsigned char* wb = p.wts + kPatchBytes + (size_t)blk * kBlockBytes;
-          mbar_wait(&bars[B_EMPTYP + ps], pphase ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&bars[B_FULLP + ps], kParamBytes);
-            bulk_g2s(smem + OFF_PARAM + ps * kParamBytes, wb, kParamBytes, &bars[B_FULLP + ps]);
-          }
-          __syncwarp();
-          if (++ps == 2) { ps = 0; pphase ^= 1; }
-          wb += kParamBytes;
-          ring_load(wb, kQkvHalfBytes); wb += kQkvHalfBytes;
-          ring_load(wb, kQkvHalfBytes); wb += kQkvHalfBytes;
-          ring_load(wb, kProjBytes); wb += kProjBytes;
-          for (int c = 0; c < 12; ++c) ring_load(wb + (size_t)c * kSlot, kSlot);   // already in consumption order
+        const unsigned char* wb = p.wts;
+        for (int c = 0; c < 4; ++c) ring_load(wb, kTile);
+        for (int blk = 0; blk < p.depth; ++blk) {                 // same order as the MMA issuer consumes (pack.cu)
+          ring_load(wb, kQkvHalfBytes + kQkvBiasBytes);
+          ring_load(wb, kQkvHalfBytes);
+          ring_load(wb, kProjBytes + kBiasTile);
+          for (int c = 0; c < 2; ++c) { ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile); }   // fc1[0], fc1[1]
+          ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile);                                     // fc2[0] (+ fc2 bias)
+          ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile);                                     // fc1[2]
+          for (int c = 0; c < 2; ++c) { ring_load(wb, kTile); ring_load(wb, kTile); }                 // fc2[1], fc2[2]
         }
       }
     }
@@ -225,7 +222,8 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     // chunk in the ring; the compute warps never block on weights, only on the completion barriers (ACC / X / FC1 / H).
     {
       const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
-      const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sVT = smem_u32(smem + OFF_VT), sP = smem_u32(smem + OFF_P);
+      const uint32_t sOnes = smem_u32(smem + OFF_CONST), sZero = sOnes + 2048;
+      const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sVT = smem_u32(smem + OFF_VT);
       constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
       constexpr uint32_t ID16 = make_idesc_bf16(128, 16);
       const bool tc_attn = p.tc_attn != 0;
@@ -245,7 +243,9 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         __syncwarp();
       };
       // KSTEPS MMAs (K = 16 each) of A[128 x 16*KSTEPS] (k-groups 2048 B apart) with the B chunk in the current ring slot
-      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, auto ksteps_c, bool accum_first) {
+      // bias_off >= 0: the slot also carries a bias tile at that byte offset -> one more k-step  D += ones * bias^T
+      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, auto ksteps_c, bool accum_first,
+                               int bias_off = -1) {
         constexpr int KSTEPS = decltype(ksteps_c)::value;
         mbar_wait(&bars[B_FULLW + cslot], cphase);
         tc_fence_after();
@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           for (int ks = 0; ks < KSTEPS; ++ks)
             umma_bf16(d_tmem, make_smem_desc(a_base + ks * 4096, 2048, 128), make_smem_desc(b_base + ks * 2 * b_lbo, b_lbo, 128), idesc,
                       (accum_first || ks > 0) ? 1u : 0u);
+          if (bias_off >= 0)
+            umma_bf16(d_tmem, make_smem_desc(sOnes, 2048, 128), make_smem_desc(b_base + bias_off, sZero - (b_base + bias_off), 128), idesc, 1u);
           umma_commit(&bars[B_EMPTYW + cslot]);
         }
         __syncwarp();
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         commit(&bars[B_ACC]);
         for (int blk = 0; blk < p.depth; ++blk) {
           wait_ready();                                                       // LN1 output in A
-          mma_from_ring(tmem + 128, sA, ID96, 1536, K4{}, false);
+          mma_from_ring(tmem + 128, sA, ID96, 1536, K4{}, false, kQkvHalfBytes);
           mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, K4{}, true);
           commit(&bars[B_ACC]);
           if (tc_attn) {                                                      // attention GEMMs (no weights involved)
@@ -285,31 +287,31 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
               wait_ready();                                                   // P_h written, S_h consumed
               if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)                                // O_h = P_h V_h  (N = 16, K = 128)
-                  umma_bf16(tmem + 128, make_smem_desc(sP + ks * 4096, 2048, 128), make_smem_desc(sVT + h * 4096 + ks * 512, 256, 128), ID16,
-                            ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < 8; ++ks)                                // O_h = P_h V_h  (N = 16, K = 128), P from TMEM
+                  umma_bf16_ts(tmem + 128 + kColO, tmem + 128 + kColP + ks * 8, make_smem_desc(sVT + h * kVtHead + ks * 2 * kVtLbo, kVtLbo, 128),
+                               ID16, ks > 0 ? 1u : 0u);
                 umma_commit(&bars[B_ACC]);
               }
               __syncwarp();
             }
           }
           wait_ready();                                                       // attention output in A_o
-          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, K2{}, true);      // x += o Wproj^T (bias deferred into cb2)
+          mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, K2{}, true, kProjBytes);   // x += o Wproj^T + bproj
           commit(&bars[B_X]);
           wait_ready();                                                       // LN2 output in A
           mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);            // fc1[0]: hidden 0..127, K half 0
-          mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true);     //                        K half 1
+          mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true, kTile);   //                     K half 1 + bias
           commit(&bars[B_FC1]);
           for (int c = 0; c < 3; ++c) {
             wait_ready();                                                     // accumulator drained into registers
             if (c < 2) {                                                      // fc1[c+1] runs while the ReLU epilogue of chunk c does
               mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);
-              mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true);
+              mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true, kTile);
               commit(&bars[B_FC1]);
             }
             wait_ready();                                                     // H (chunk c) written
             mma_from_ring(tmem, sH, ID128, 2048, K4{}, true);                 // fc2[c]: x += H_c W2_c^T  (K = 128 hidden)
-            mma_from_ring(tmem, sH + 16384, ID128, 2048, K4{}, true);
+            mma_from_ring(tmem, sH + 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // + fc2 bias, once
             commit(&bars[B_H]);
           }
         }
@@ -321,7 +323,6 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     const int r = q * 32 + lane;                                   // row == TMEM lane
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
     const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
-    uint32_t ps = 0, pphase = 0;          // param slot
     uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0;
     uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
 #ifdef UITK_TRACE
@@ -422,13 +423,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 
       // ---------------- transformer blocks ----------------
       for (int blk = 0; blk < p.depth; ++blk) {
-        mbar_wait_all(&bars[B_FULLP + ps], pphase);
-        const float* prm = reinterpret_cast<const float*>(smem + OFF_PARAM + ps * kParamBytes);
         TR(0, 10);
-        const float *cb1 = prm + 256, *qkv_b = prm + 384, *cb2 = prm + 768, *b1 = prm + 896;   // LN affine is folded into W/b
 
         // LN1 -> A ; qkv = A Wqkv^T  (two K halves through the ring)
-        ln_to_operand(tx, hsel, r, cb1, 1e-6f, part, smem + OFF_A);
+        ln_to_operand(tx, hsel, r, 1e-6f, part, smem + OFF_A);
         signal_ready();
         TR(0, 11);
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
@@ -440,21 +438,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           const int g = valid ? r / 24 : 0;
           const int cbase = g * 24;                                   // this row's keys = S columns [cbase, cbase + 24)
           {   // qkv (+bias) -> bf16 operands.  hsel 0 holds q(32) k_h0(16); hsel 1 holds k_h1(16) v(32)
-            const float* bq = qkv_b + hsel * 48;
             float v[32], w[16];
             tmem_ld32(tacc + hsel * 48, v);
             tmem_ld16(tacc + hsel * 48 + 32, w);
             tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bq + 32 + i);
-              w[i] += b4.x; w[i + 1] += b4.y; w[i + 2] += b4.z; w[i + 3] += b4.w;
-            }
             if (hsel == 0) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)                               // q: head c>>1, k-group c&1
@@ -466,11 +453,11 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 #pragma unroll
               for (int c = 0; c < 2; ++c)                               // k, head 1
                 *reinterpret_cast<uint4*>(smem + OFF_K + 4096 + c * 2048 + r * 16) = pack8_bf16(v + c * 8);
-              unsigned char* vt = smem + OFF_VT + (r >> 3) * 256 + (r & 7) * 2;      // V^T[d][key r]
+              unsigned char* vt = smem + OFF_VT + (r >> 3) * kVtLbo + (r & 7) * 2;   // V^T[d][key r]
 #pragma unroll
               for (int d = 0; d < 16; ++d) {
                 *reinterpret_cast<__nv_bfloat16*>(vt + d * 16) = __float2bfloat16_rn(v[16 + d]);            // head 0
-                *reinterpret_cast<__nv_bfloat16*>(vt + 4096 + d * 16) = __float2bfloat16_rn(w[d]);          // head 1
+                *reinterpret_cast<__nv_bfloat16*>(vt + kVtHead + d * 16) = __float2bfloat16_rn(w[d]);       // head 1
               }
             }
           }
@@ -518,31 +505,35 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             const float f = valid ? f_own / (l_loc * f_own + oth.y * f_oth) : 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) sv[i] *= f;
-            unsigned char* P = smem + OFF_P + r * 16;
-            const int c0 = valid ? 3 * g : 99;                            // value chunks c0 .. c0+2 (none for padding rows)
+            // P_h -> tensor memory.  Row r holds its clip's 24 probabilities in packed columns [12 g, 12 g + 12) and zeros
+            // elsewhere.  tcgen05.st takes one (warp-uniform) column address, so every clip's column block is stored by the
+            // whole warp: lanes of that clip store their values, all other lanes zeros (this thread: 8 of the 12 columns
+            // for hsel 0, the last 4 for hsel 1, which also clears the 4 tail columns).  All S_h reads of the CTA happened
+            // before the exchange barrier above, so overwriting S_h is safe.
+            uint32_t pk[8];
 #pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8) {
-              const int kk = hsel * 8 + k8;
-              if (kk < c0 || kk > c0 + 2) *reinterpret_cast<uint4*>(P + kk * 2048) = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 8; ++j) pk[j] = pack2_bf16(sv[2 * j], sv[2 * j + 1]);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              const bool mine = valid && g == c;
+              uint32_t z[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) z[j] = mine ? pk[j] : 0u;
+              if (hsel == 0) { tmem_st4(tacc + kColP + 12 * c, z); tmem_st4(tacc + kColP + 12 * c + 4, z + 4); }
+              else tmem_st4(tacc + kColP + 12 * c + 8, z);
             }
-            if (valid) {
-              if (hsel == 0) {
-                *reinterpret_cast<uint4*>(P + c0 * 2048) = pack8_bf16(sv);
-                *reinterpret_cast<uint4*>(P + (c0 + 1) * 2048) = pack8_bf16(sv + 8);
-              } else {
-                *reinterpret_cast<uint4*>(P + (c0 + 2) * 2048) = pack8_bf16(sv);
-              }
-            }
-            signal_ready();                                               // P_h complete, S_h consumed
+            if (hsel == 1) { const uint32_t z[4] = {0u, 0u, 0u, 0u}; tmem_st4(tacc + kColP + 60, z); }
+            tmem_st_wait();
+            signal_drained();                                             // P_h complete (tensor memory), S_h consumed
             TR(0, 15);
-            mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // O_h in ACC columns 0..15
+            mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // O_h in ACC columns 64..79
             tc_fence_after();
             TR(0, 16);
             float o[8];
-            tmem_ld8(tacc + hsel * 8, o);
+            tmem_ld8(tacc + kColO + hsel * 8, o);
             tmem_ld_wait();
             *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + hsel) * 2048 + r * 16) = pack8_bf16(o);
-            if (h == 0) signal_ready();                                   // ACC drained: S_1 may overwrite it
+            if (h == 0) signal_drained();                                 // ACC drained: S_1 may overwrite it
             TR(0, 17);
           }
         } else {
@@ -550,23 +541,16 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           // rows of different clips are 24*400 B apart = the same banks: a 16-B pad per clip lets the two clips a warp
           // straddles be served in one wavefront when the attention threads broadcast-read k/v rows
           float* dstq = reinterpret_cast<float*>(smem + OFF_QKV) + r * QKV_LD + (r / tokens) * 4 + hsel * 48;
-          const float* bq = qkv_b + hsel * 48;
           float v[32];
           tmem_ld32(tacc + hsel * 48, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-            *reinterpret_cast<float4*>(dstq + i) = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
-          }
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dstq + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           float w[16];
           tmem_ld16(tacc + hsel * 48 + 32, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bq + 32 + i);
-            *reinterpret_cast<float4*>(dstq + 32 + i) = make_float4(w[i] + b4.x, w[i + 1] + b4.y, w[i + 2] + b4.z, w[i + 3] + b4.w);
-          }
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dstq + 32 + i) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
         }
         tc_fence_before();
         bar_compute();
@@ -639,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         TR(0, 19);
 
         // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
-        ln_to_operand(tx, hsel, r, cb2, 1e-6f, part + 512, smem + OFF_A);
+        ln_to_operand(tx, hsel, r, 1e-6f, part + 512, smem + OFF_A);
         signal_ready();
         TR(0, 20);
 #pragma unroll 1
@@ -655,11 +639,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           TR(0, 24);
           if (c >= 1) { mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1; }     // fc2[c-1] finished reading H
           unsigned char* H = smem + OFF_H + hsel * 16384 + r * 16;
-          const float* bb = b1 + c * 128 + hsel * 64;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = bias_relu_pack8(v0 + cc * 8, bb + cc * 8);
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = relu_pack8(v0 + cc * 8);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + (4 + cc) * 2048) = bias_relu_pack8(v1 + cc * 8, bb + 32 + cc * 8);
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + (4 + cc) * 2048) = relu_pack8(v1 + cc * 8);
           signal_ready();
           TR(0, 22);
         }
@@ -667,16 +650,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1;
         tc_fence_after();
         TR(0, 23);
-        if (tid == 0) mbar_arrive(&bars[B_EMPTYP + ps]);
-        __syncwarp();
-        if (++ps == 2) { ps = 0; pphase ^= 1; }
       }
 
       // ---------------- final LayerNorm (eps 1e-6) + token mean -> pooled[rr][128] ----------------
       {
         float* Y = reinterpret_cast<float*>(smem + OFF_A);      // [128][128] fp32 over A|H, 16-B chunks XOR-swizzled by row
         float mean, rstd;
-        row_stats(tx, hsel, r, p.cb_final, 1e-6f, part, mean, rstd);
+        row_stats(tx, hsel, r, 1e-6f, part, mean, rstd);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float v[32];
@@ -685,10 +665,9 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const int k = hsel * 64 + j * 32 + i;
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cb_final + k));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k));
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.norm_b + k));
-            const float x0 = v[i] + c4.x, x1 = v[i + 1] + c4.y, x2 = v[i + 2] + c4.z, x3 = v[i + 3] + c4.w;
+            const float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
             if (p.dbg_x != nullptr && r < rows_valid)
               *reinterpret_cast<float4*>(p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + k) = make_float4(x0, x1, x2, x3);
             float4 o;
@@ -772,7 +751,7 @@ int run_encoder_tc(const EncoderArgs& a) {
   p.wts = blob + bf16_off;
   p.patch_b = W + lay.patch_b; p.time_pos = W + lay.time_pos; p.freq_pos = W + lay.freq_pos;
   p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift;
-  p.norm_w = W + lay.norm_w; p.norm_b = W + lay.norm_b; p.cb_final = W + lay.cb_final;
+  p.norm_w = W + lay.norm_w; p.norm_b = W + lay.norm_b;
   p.db = a.db; p.max_pow = a.max_pow;
   p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
   p.RR = (int)RR; p.G = 128 / tokens; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;

@@ -89,6 +89,26 @@ static void pack_kmajor(uint16_t* dst, const float* W, int ldw, int n0, int N, i
       for (int i = 0; i < 8; ++i) dst[((size_t)k8 * N + n) * 8 + i] = f2bf(W[(size_t)(n0 + n) * ldw + k0 + k8 * 8 + i]);
 }
 
+static float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// [N x 8] bf16 tile (one K-major k-group): row n = (hi, mid, lo, 0, 0, 0, 0, 0) with hi + mid + lo == bias[n] to ~2^-24
+static void pack_bias_tile(uint16_t* dst, const float* bias, int N) {
+  for (int n = 0; n < N; ++n) {
+    const uint16_t hi = f2bf(bias[n]);
+    const float r1 = bias[n] - bf2f(hi);
+    const uint16_t mid = f2bf(r1);
+    const uint16_t lo = f2bf(r1 - bf2f(mid));
+    uint16_t* d = dst + (size_t)n * 8;
+    d[0] = hi; d[1] = mid; d[2] = lo;
+    for (int i = 3; i < 8; ++i) d[i] = 0;
+  }
+}
+
 static size_t fp32_section_bytes(const EncoderLayout& l) { return (l.total_floats * sizeof(float) + 1023) / 1024 * 1024; }
 
 }  // namespace uitk
@@ -239,36 +259,42 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
     if (cfg->precision == UITK_PREC_BF16) {
       unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();   // after the 4 x 16 KB patch chunks
-      float* prm = reinterpret_cast<float*>(blk);
       // LayerNorm affine folded into the consuming Linear: W' = W diag(gamma), b' = b + W beta (fp32, then bf16 for W')
-      std::vector<float> wq(96 * 128), w1f(384 * 128);
+      std::vector<float> wq(96 * 128), w1f(384 * 128), bq(96), b1f(384);
       for (int o = 0; o < 96; ++o) {
         float acc = b[3][o];
         for (int k = 0; k < 128; ++k) { wq[o * 128 + k] = b[2][o * 128 + k] * b[0][k]; acc += b[2][o * 128 + k] * b[1][k]; }
-        prm[384 + o] = acc;                                                    // qkv bias'
+        bq[o] = acc;                                                            // qkv bias'
       }
       for (int o = 0; o < 384; ++o) {
         float acc = b[9][o];
         for (int k = 0; k < 128; ++k) { w1f[o * 128 + k] = b[8][o * 128 + k] * b[6][k]; acc += b[8][o * 128 + k] * b[7][k]; }
-        prm[896 + o] = acc;                                                    // fc1 bias'
+        b1f[o] = acc;                                                           // fc1 bias'
       }
-      memcpy(prm + 0, b[0], 128 * 4); memcpy(prm + 128, b[1], 128 * 4);        // ln1 w, b (kept for reference; unused by the kernel)
-      memcpy(prm + 256, cb.data(), 128 * 4);                                   // cb1
-      memcpy(prm + 512, b[6], 128 * 4); memcpy(prm + 640, b[7], 128 * 4);      // ln2 w, b (unused by the kernel)
-      for (int c = 0; c < 128; ++c) prm[768 + c] = cb[c] + b[5][c];            // cb2 = cb1 + proj bias
-      // weight chunks in the order the kernel consumes them (csrc/encoder_tc.cu)
-      uint16_t* w = reinterpret_cast<uint16_t*>(blk + 1280 * 4);
-      pack_kmajor(w, wq.data(), 128, 0, 96, 0, 64); w += 96 * 64;               // Wqkv' [96][128], K half 0
-      pack_kmajor(w, wq.data(), 128, 0, 96, 64, 64); w += 96 * 64;              // Wqkv', K half 1
-      pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // Wproj [128][32]
-      // MLP in 3 chunks of 128 hidden units; every 16 KB ring slot is one [128 x 64] K-major tile (4 MMA k-steps)
-      auto w1 = [&](int c) {                                                     // fc1' rows 128c.., K halves
+      // Ring slots in the order the kernel consumes them (csrc/encoder_tc.cu).  Every Linear bias rides along as a
+      // [N x 8] bf16 "bias tile" (hi, mid, lo split of the fp32 value in k = 0..2) that one extra MMA k-step multiplies
+      // with a constant ones operand: the CUDA cores never touch a bias.
+      uint16_t* w = reinterpret_cast<uint16_t*>(blk);
+      pack_kmajor(w, wq.data(), 128, 0, 96, 0, 64); w += 96 * 64;               // slot: Wqkv' [96][128] K half 0 ...
+      pack_bias_tile(w, bq.data(), 96); w += 96 * 8;                            //       ... + qkv bias' tile
+      pack_kmajor(w, wq.data(), 128, 0, 96, 64, 64); w += 96 * 64;              // slot: Wqkv' K half 1
+      pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // slot: Wproj [128][32] ...
+      pack_bias_tile(w, b[5], 128); w += 128 * 8;                               //       ... + proj bias tile
+      // MLP in 3 chunks of 128 hidden units; weight tiles are [128 x 64] K-major (4 MMA k-steps)
+      auto w1 = [&](int c) {                                                     // fc1' rows 128c.., K halves, + bias' tile
         for (int kh = 0; kh < 2; ++kh) { pack_kmajor(w, w1f.data(), 128, c * 128, 128, kh * 64, 64); w += 128 * 64; }
+        pack_bias_tile(w, b1f.data() + c * 128, 128); w += 128 * 8;
       };
-      auto w2 = [&](int c) {                                                     // fc2 K slices 128c + 64hh ..
+      auto w2 = [&](int c) {                                                     // fc2 K slices 128c + 64hh .. (+ fc2 bias tile once)
         for (int hh = 0; hh < 2; ++hh) { pack_kmajor(w, b[10], 384, 0, 128, c * 128 + hh * 64, 64); w += 128 * 64; }
+        if (c == 0) { pack_bias_tile(w, b[11], 128); w += 128 * 8; }
       };
       w1(0); w1(1); w2(0); w1(2); w2(1); w2(2);
+      if ((size_t)(reinterpret_cast<unsigned char*>(w) - blk) != encoder_tc_block_bytes()) {
+        set_error("internal: packed block is %zu bytes, kernel expects %zu", (size_t)(reinterpret_cast<unsigned char*>(w) - blk),
+                  encoder_tc_block_bytes());
+        return UITK_EINVAL;
+      }
     }
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
   }

@@ -100,6 +100,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : A operand read from TENSOR MEMORY (row m = lane m, two bf16 per 32-bit column,
+// element 2j in the low half: K = 16 per instruction = 8 columns).  No shared-memory read for A, no proxy fence.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // mbarrier arrives when all tcgen05 async ops previously issued by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -151,6 +162,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2): two IEEE fp32 ops per issued instruction ----------
@@ -190,6 +204,11 @@ __device__ __forceinline__ uint32_t pack2_relu_bf16(float lo, float hi) {
   uint32_t o;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
   return o;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
 }
 
 // pack 8 fp32 -> 8 bf16 (round to nearest even) as one 16-byte chunk
