@@ -92,15 +92,31 @@ __device__ long long g_trace[2][4096];
 #endif
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two warps that share TMEM lane quarter q (hsel 0 / 1): the only threads that exchange per-row partial results
+__device__ __forceinline__ void bar_pair(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // wait executed by every thread of a warp: re-converge before the .sync.aligned tcgen05 instructions that follow
 __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
   mbar_wait(bar, parity);
   __syncwarp();
 }
 
-// Row statistics of this thread's row of x in ONE pass (sum and sum of squares; var = E[x^2] - mean^2 in fp32: |mean| is
-// O(std) for these activations, the cancellation costs < 1e-6 relative).  The two threads of a row (hsel 0/1) each
-// reduce 64 columns and exchange partial sums through `part` with a single barrier.
+// Exchange of the two half-row partial sums (sum, sum of squares) of a row through `part`, mean / rstd of the full row.
+// var = E[x^2] - mean^2 in fp32: |mean| is O(std) for these activations, the cancellation costs < 1e-6 relative.
+__device__ __forceinline__ void finish_stats(float s, float ss, int hsel, int r, float eps, float* part, float& mean, float& rstd) {
+  *reinterpret_cast<float2*>(part + (hsel * 128 + r) * 2) = make_float2(s, ss);
+  bar_pair(r >> 5);
+  const float2 oth = *reinterpret_cast<const float2*>(part + ((hsel ^ 1) * 128 + r) * 2);
+  mean = (s + oth.x) * (1.f / 128.f);
+  const float var = fmaxf((ss + oth.y) * (1.f / 128.f) - mean * mean, 0.f);
+  rstd = rsqrtf(var + eps);
+}
+
+// Row statistics of this thread's row of x (two threads per row, 64 columns each), values not kept.
 __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, float eps, float* part, float& mean, float& rstd) {
   float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);     // packed fp32x2 accumulators (even, odd columns)
 #pragma unroll
@@ -115,37 +131,48 @@ __device__ __forceinline__ void row_stats(uint32_t tx, int hsel, int r, float ep
       q2 = fma2(xa, xa, q2);
     }
   }
-  const float s = s2.x + s2.y, ss = q2.x + q2.y;
-  *reinterpret_cast<float2*>(part + (hsel * 128 + r) * 2) = make_float2(s, ss);
-  bar_compute();
-  const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (128 + r) * 2);
-  mean = (p0.x + p1.x) * (1.f / 128.f);
-  const float var = fmaxf((p0.y + p1.y) * (1.f / 128.f) - mean * mean, 0.f);
-  rstd = rsqrtf(var + eps);
+  finish_stats(s2.x + s2.y, q2.x + q2.y, hsel, r, eps, part, mean, rstd);
 }
 
-// LayerNorm of this thread's half row straight out of TMEM, written as bf16 K-major core-matrix chunks.
+// LayerNorm of this thread's half row straight out of TMEM (ONE read: the 64 values stay in registers between the
+// statistics and the normalisation), written as bf16 K-major core-matrix chunks.
 // Only the normalisation (x - mean) * rstd happens here: the affine part (gamma, beta) is folded into the weights
 // and bias of the Linear that consumes the operand when the weights are packed (W' = W diag(gamma), b' = b + W beta).
 __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, float eps, float* part, unsigned char* dst) {
+  float v0[32], v1[32];
+  tmem_ld32(tx + hsel * 64, v0);
+  tmem_ld32(tx + hsel * 64 + 32, v1);
+  tmem_ld_wait();
+  float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;       // independent chains
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 xa = make_float2(v0[i], v0[i + 1]), xb = make_float2(v1[i], v1[i + 1]);
+    sa = add2(sa, xa); sb = add2(sb, xb);
+    qa = fma2(xa, xa, qa); qb = fma2(xb, xb, qb);
+  }
   float mean, rstd;
-  row_stats(tx, hsel, r, eps, part, mean, rstd);
+  finish_stats((sa.x + sa.y) + (sb.x + sb.y), (qa.x + qa.y) + (qb.x + qb.y), hsel, r, eps, part, mean, rstd);
   const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
+  unsigned char* d = dst + hsel * 8 * 2048 + r * 16;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    float v[32];
-    tmem_ld32(tx + hsel * 64 + j * 32, v);
-    tmem_ld_wait();
+  for (int c = 0; c < 4; ++c) {
+    uint4 o;
+    float2 y;
+    y = fma2(make_float2(v0[c * 8 + 0], v0[c * 8 + 1]), rs2, nm2); o.x = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v0[c * 8 + 2], v0[c * 8 + 3]), rs2, nm2); o.y = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v0[c * 8 + 4], v0[c * 8 + 5]), rs2, nm2); o.z = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v0[c * 8 + 6], v0[c * 8 + 7]), rs2, nm2); o.w = pack2_bf16(y.x, y.y);
+    *reinterpret_cast<uint4*>(d + c * 2048) = o;
+  }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float y[8];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float2 ya = fma2(make_float2(v[c * 8 + 2 * h], v[c * 8 + 2 * h + 1]), rs2, nm2);
-        y[2 * h] = ya.x; y[2 * h + 1] = ya.y;
-      }
-      *reinterpret_cast<uint4*>(dst + (hsel * 8 + j * 4 + c) * 2048 + r * 16) = pack8_bf16(y);
-    }
+  for (int c = 0; c < 4; ++c) {
+    uint4 o;
+    float2 y;
+    y = fma2(make_float2(v1[c * 8 + 0], v1[c * 8 + 1]), rs2, nm2); o.x = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v1[c * 8 + 2], v1[c * 8 + 3]), rs2, nm2); o.y = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v1[c * 8 + 4], v1[c * 8 + 5]), rs2, nm2); o.z = pack2_bf16(y.x, y.y);
+    y = fma2(make_float2(v1[c * 8 + 6], v1[c * 8 + 7]), rs2, nm2); o.w = pack2_bf16(y.x, y.y);
+    *reinterpret_cast<uint4*>(d + (4 + c) * 2048) = o;
   }
 }
 
@@ -489,20 +516,28 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
                 }
               }
             }
-            const int n = hsel == 0 ? 16 : 8;
-            float m_loc = -INFINITY;
+            // hsel 0 owns keys 0..15 of the clip, hsel 1 keys 16..23 (sv[8..15] unused there); tree reductions for ILP
+            float m_loc, l_loc;
+            {
+              float m8[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (i < n) m_loc = fmaxf(m_loc, sv[i]);
-            float l_loc = 0.f;
+              for (int i = 0; i < 8; ++i) m8[i] = hsel == 0 ? fmaxf(sv[i], sv[i + 8]) : sv[i];
+              m_loc = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+              const float mb = -m_loc * kScaleLog2e;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (i < n) { sv[i] = exp2f((sv[i] - m_loc) * kScaleLog2e); l_loc += sv[i]; }
+              for (int i = 0; i < 16; ++i) sv[i] = (hsel == 0 || i < 8) ? ex2_approx(fmaf(sv[i], kScaleLog2e, mb)) : 0.f;
+              float s8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s8[i] = sv[i] + sv[i + 8];
+              l_loc = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+            }
             float* ex = part + h * 512;
             *reinterpret_cast<float2*>(ex + (hsel * 128 + r) * 2) = make_float2(m_loc, l_loc);
-            bar_compute();
+            bar_pair(q);       // the partner thread of this row is in the other warp of the pair; its S_h reads are done too
             const float2 oth = *reinterpret_cast<const float2*>(ex + ((hsel ^ 1) * 128 + r) * 2);
             const float M = fmaxf(m_loc, oth.x);
-            const float f_own = exp2f((m_loc - M) * kScaleLog2e), f_oth = exp2f((oth.x - M) * kScaleLog2e);
-            const float f = valid ? f_own / (l_loc * f_own + oth.y * f_oth) : 0.f;
+            const float f_own = ex2_approx((m_loc - M) * kScaleLog2e), f_oth = ex2_approx((oth.x - M) * kScaleLog2e);
+            const float f = valid ? __fdividef(f_own, l_loc * f_own + oth.y * f_oth) : 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) sv[i] *= f;
             // P_h -> tensor memory.  Row r holds its clip's 24 probabilities in packed columns [12 g, 12 g + 12) and zeros
@@ -637,12 +672,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           tmem_ld_wait();
           signal_drained();                                               // fc1[c+1] may overwrite the accumulator
           TR(0, 24);
+          uint4 hv[8];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) { hv[cc] = relu_pack8(v0 + cc * 8); hv[4 + cc] = relu_pack8(v1 + cc * 8); }
           if (c >= 1) { mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1; }     // fc2[c-1] finished reading H
           unsigned char* H = smem + OFF_H + hsel * 16384 + r * 16;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = relu_pack8(v0 + cc * 8);
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + (4 + cc) * 2048) = relu_pack8(v1 + cc * 8);
+          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = hv[cc];
           signal_ready();
           TR(0, 22);
         }
