@@ -37,8 +37,9 @@ constexpr int kSlots = 2;
 constexpr uint32_t kQkvHalfBytes = 96 * 64 * 2;       // Wqkv, one K half: 12288
 constexpr uint32_t kQkvBiasBytes = 96 * 16;           // 1536
 constexpr uint32_t kProjBytes = 128 * 32 * 2;         // 8192
-// per block: [Wqkv k0 | bqkv] [Wqkv k1] [Wproj | bproj]  3 x ([W1 k0] [W1 k1 | b1])  3 x ([W2 h0] [W2 h1]) (+ b2 after the first)
-constexpr uint32_t kBlockBytes = 2 * kQkvHalfBytes + kQkvBiasBytes + kProjBytes + kBiasTile + 3 * (2 * kTile + kBiasTile) + 6 * kTile + kBiasTile;
+constexpr uint32_t kFc1BiasBytes = 64 * 16;           // bias tile of one 64-column fc1 chunk
+// per block: [Wqkv k0 | bqkv] [Wqkv k1] [Wproj | bproj]  6 x [W1 chunk | b1 chunk]  6 x [W2 chunk] (+ b2 behind the first)
+constexpr uint32_t kBlockBytes = 2 * kQkvHalfBytes + kQkvBiasBytes + kProjBytes + kBiasTile + 6 * (kTile + kFc1BiasBytes) + 6 * kTile + kBiasTile;
 constexpr uint32_t kPatchBytes = 4 * kTile;           // 4 K-quarters of the patch weight
 
 // shared memory map (bytes); one CTA uses 108.3 KB so that two fit on an SM
@@ -57,6 +58,8 @@ constexpr uint32_t kVtLbo = 272, kVtHead = 16 * kVtLbo;
 // columns 0..63, packed bf16 pairs, over the dead S_h) and is the TMEM A operand of the P V product; O_h lands in
 // accumulator columns 64..79.
 constexpr uint32_t kColP = 0, kColO = 64;
+// MLP phase: fc1 chunk accumulator (64 fp32 columns) and the LayerNorm-2 output as packed-bf16 TMEM A operand (64 columns)
+constexpr uint32_t kColFc1 = 0, kColLn2 = 64;
 constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
 // constant MMA operands: k-group of (1, 1, 1, 0, ..) rows = the A operand of every bias k-step, then 2 KB of zeros that
 // serve as the second k-group of both the ones operand and every bias tile (their LBO points here: it must lie ABOVE the ring)
@@ -67,7 +70,7 @@ constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = 2, B_ACC = 4, B_X = 5, B_FC1 = 6, B_H = 7, B_READY = 8, B_COUNT = 10 };
+enum { B_FULLW = 0, B_EMPTYW = 2, B_ACC = 4, B_X = 5, B_FC1 = 6, B_H = 7 /* 4 hidden slots */, B_COUNT = 11 };
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
@@ -94,11 +97,14 @@ __device__ long long g_trace[2][4096];
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // the two warps that share TMEM lane quarter q (hsel 0 / 1): the only threads that exchange per-row partial results
 __device__ __forceinline__ void bar_pair(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
-// compute warps -> MMA issuer hand-off on a named barrier (ids 6 / 7 alternate): the 256 compute threads arrive without
+// compute warps -> MMA issuer hand-off on named barriers (ids 6..9 in rotation): the 256 compute threads arrive without
 // blocking, the 32 issuer threads sync.  A named-barrier release costs ~30 cycles against ~140 for an mbarrier wake-up.
+// FOUR ids: in the MLP the compute warps can be up to three signals ahead of the issuer (H-ready(c) still unconsumed while
+// drained(c+1) and H-ready(c+1) arrive; the next signal needs fc1[c+2], which the issuer only issues after consuming
+// drained(c+1)), and a barrier id must never collect arrivals of two signals at once.
 constexpr int kReadyThreads = kCompute + 32;
-__device__ __forceinline__ void ready_arrive(uint32_t sig) { asm volatile("bar.arrive %0, %1;" ::"r"(6 + (sig & 1)), "n"(kReadyThreads) : "memory"); }
-__device__ __forceinline__ void ready_sync(uint32_t sig) { asm volatile("bar.sync %0, %1;" ::"r"(6 + (sig & 1)), "n"(kReadyThreads) : "memory"); }
+__device__ __forceinline__ void ready_arrive(uint32_t sig) { asm volatile("bar.arrive %0, %1;" ::"r"(6 + (sig & 3)), "n"(kReadyThreads) : "memory"); }
+__device__ __forceinline__ void ready_sync(uint32_t sig) { asm volatile("bar.sync %0, %1;" ::"r"(6 + (sig & 3)), "n"(kReadyThreads) : "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -181,6 +187,35 @@ __device__ __forceinline__ void ln_to_operand(uint32_t tx, int hsel, int r, floa
   }
 }
 
+// Same LayerNorm, but the normalised half row goes to TENSOR MEMORY as packed bf16 pairs (32 columns per thread, ONE
+// tcgen05.st): the A operand of a TS-mode tcgen05.mma.  No shared-memory traffic and no proxy fence.
+__device__ __forceinline__ void ln_to_tmem(uint32_t tx, uint32_t tdst, int hsel, int r, float eps, float* part) {
+  float v0[32], v1[32];
+  tmem_ld32(tx + hsel * 64, v0);
+  tmem_ld32(tx + hsel * 64 + 32, v1);
+  tmem_ld_wait();
+  float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 xa = make_float2(v0[i], v0[i + 1]), xb = make_float2(v1[i], v1[i + 1]);
+    sa = add2(sa, xa); sb = add2(sb, xb);
+    qa = fma2(xa, xa, qa); qb = fma2(xb, xb, qb);
+  }
+  float mean, rstd;
+  finish_stats((sa.x + sa.y) + (sb.x + sb.y), (qa.x + qa.y) + (qb.x + qb.y), hsel, r, eps, part, mean, rstd);
+  const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
+  float pk[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 ya = fma2(make_float2(v0[2 * i], v0[2 * i + 1]), rs2, nm2);
+    const float2 yb = fma2(make_float2(v1[2 * i], v1[2 * i + 1]), rs2, nm2);
+    pk[i] = __uint_as_float(pack2_bf16(ya.x, ya.y));
+    pk[16 + i] = __uint_as_float(pack2_bf16(yb.x, yb.y));
+  }
+  tmem_st32(tdst + hsel * 32, pk);
+  tmem_st_wait();
+}
+
 // relu(v) for 8 consecutive hidden columns -> one 16-byte bf16 chunk (the fc1 bias is already in the accumulator)
 __device__ __forceinline__ uint4 relu_pack8(const float* v) {
   uint4 o;
@@ -199,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches stay uniform
 
   if (tid == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_READY || i == B_READY + 1) ? kCompute / 32 : 1);   // one arrive per compute warp
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -237,10 +272,11 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           ring_load(wb, kQkvHalfBytes + kQkvBiasBytes);
           ring_load(wb, kQkvHalfBytes);
           ring_load(wb, kProjBytes + kBiasTile);
-          for (int c = 0; c < 2; ++c) { ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile); }   // fc1[0], fc1[1]
-          ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile);                                     // fc2[0] (+ fc2 bias)
-          ring_load(wb, kTile); ring_load(wb, kTile + kBiasTile);                                     // fc1[2]
-          for (int c = 0; c < 2; ++c) { ring_load(wb, kTile); ring_load(wb, kTile); }                 // fc2[1], fc2[2]
+          ring_load(wb, kTile + kFc1BiasBytes);                                                      // fc1[0]
+          for (int c = 0; c < 6; ++c) {
+            if (c < 5) ring_load(wb, kTile + kFc1BiasBytes);                                          // fc1[c+1]
+            ring_load(wb, kTile + (c == 0 ? kBiasTile : 0u));                                         // fc2[c] (+ fc2 bias once)
+          }
         }
       }
     }
@@ -280,13 +316,16 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       };
       // KSTEPS MMAs (K = 16 each) of A[128 x 16*KSTEPS] (k-groups 2048 B apart) with the B chunk in the current ring slot
       // bias_off >= 0: the slot also carries a bias tile at that byte offset -> one more k-step  D += ones * bias^T
-      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, auto ksteps_c, bool accum_first,
-                               int bias_off = -1) {
-        constexpr int KSTEPS = decltype(ksteps_c)::value;
+      auto mbar_wait_ring = [&]() {
         if (!prewaited) mbar_wait(&bars[B_FULLW + cslot], cphase);
         prewaited = false;
         tc_fence_after();
         TR(1, 2);
+      };
+      auto mma_from_ring = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, uint32_t b_lbo, auto ksteps_c, bool accum_first,
+                               int bias_off = -1) {
+        constexpr int KSTEPS = decltype(ksteps_c)::value;
+        mbar_wait_ring();
         const uint32_t b_base = sRing + cslot * kSlot;
         if (elect_one()) {
 #pragma unroll
@@ -335,21 +374,31 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           wait_ready();                                                       // attention output in A_o
           mma_from_ring(tmem, sA /* == A_o */, ID128, 2048, K2{}, true, kProjBytes);   // x += o Wproj^T + bproj
           commit(&bars[B_X]);
-          wait_ready();                                                       // LN2 output in A
-          mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);            // fc1[0]: hidden 0..127, K half 0
-          mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true, kTile);   //                     K half 1 + bias
-          commit(&bars[B_FC1]);
-          for (int c = 0; c < 3; ++c) {
-            wait_ready();                                                     // accumulator drained into registers
-            if (c < 2) {                                                      // fc1[c+1] runs while the ReLU epilogue of chunk c does
-              mma_from_ring(tmem + 128, sA, ID128, 2048, K4{}, false);
-              mma_from_ring(tmem + 128, sA + 16384, ID128, 2048, K4{}, true, kTile);
-              commit(&bars[B_FC1]);
+          wait_ready();                                                       // LN2 output in tensor memory (acc columns 64..127)
+          // MLP in 6 chunks of 64 hidden units.  fc1 reads its A operand (the LayerNorm output, packed bf16) from TENSOR
+          // MEMORY: no shared-memory A traffic, and at N = 64 a TS-mode k-step takes 32 cycles (SS mode: 48, SMEM-bound).
+          auto fc1 = [&]() {
+            mbar_wait_ring();
+            const uint32_t b_base = sRing + cslot * kSlot;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16_ts(tmem + 128 + kColFc1, tmem + 128 + kColLn2 + ks * 8, make_smem_desc(b_base + ks * 2048, 1024, 128), ID64, ks > 0 ? 1u : 0u);
+              umma_bf16(tmem + 128 + kColFc1, make_smem_desc(sOnes, 2048, 128), make_smem_desc(b_base + kTile, sZero - (b_base + kTile), 128), ID64, 1u);
+              umma_commit(&bars[B_EMPTYW + cslot]);
+              umma_commit(&bars[B_FC1]);
             }
-            wait_ready();                                                     // H (chunk c) written
-            mma_from_ring(tmem, sH, ID128, 2048, K4{}, true);                 // fc2[c]: x += H_c W2_c^T  (K = 128 hidden)
-            mma_from_ring(tmem, sH + 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // + fc2 bias, once
-            commit(&bars[B_H]);
+            __syncwarp();
+            TR(1, 3);
+            if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
+          };
+          fc1();
+          for (int c = 0; c < 6; ++c) {
+            wait_ready();                                                     // accumulator drained into registers
+            if (c < 5) fc1();                                                 // fc1[c+1] runs while the ReLU epilogue of chunk c does
+            wait_ready();                                                     // H slot c & 3 written
+            mma_from_ring(tmem, sA + (c & 3) * 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // fc2[c]: x += H_c W2_c^T (+ b2 once)
+            commit(&bars[B_H + (c & 3)]);
           }
         }
       }
@@ -360,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     const int r = q * 32 + lane;                                   // row == TMEM lane
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
     const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
-    uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0;
+    uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0;      // ph_h: one phase bit per hidden slot
     uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
 #ifdef UITK_TRACE
     const bool trace_on = blockIdx.x == 0 && tid == 0;
@@ -665,33 +714,34 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         tc_fence_after();
         TR(0, 19);
 
-        // LN2 -> A ; 6 hidden chunks: hidden_c = relu(A W1_c^T + b1_c) ; x += hidden_c W2_c^T
-        ln_to_operand(tx, hsel, r, 1e-6f, part + 512, smem + OFF_A);
-        signal_ready();
+        // LN2 -> tensor memory ; 6 hidden chunks: hidden_c = relu(LN2 W1_c^T + b1_c) ; x += hidden_c W2_c^T
+        ln_to_tmem(tx, tacc + kColLn2, hsel, r, 1e-6f, part + 512);
+        signal_drained();                  // nothing went to shared memory: no proxy fence
         TR(0, 20);
 #pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 6; ++c) {
           mbar_wait_all(&bars[B_FC1], ph_fc1); ph_fc1 ^= 1;
           tc_fence_after();
           TR(0, 21);
-          float v0[32], v1[32];                                           // this thread's 64 hidden columns of the chunk
-          tmem_ld32(tacc + hsel * 64, v0);
-          tmem_ld32(tacc + hsel * 64 + 32, v1);
+          float v[32];                                                    // this thread's 32 hidden columns of the chunk
+          tmem_ld32(tacc + kColFc1 + hsel * 32, v);
           tmem_ld_wait();
           signal_drained();                                               // fc1[c+1] may overwrite the accumulator
           TR(0, 24);
-          uint4 hv[8];
+          uint4 hv[4];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) { hv[cc] = relu_pack8(v0 + cc * 8); hv[4 + cc] = relu_pack8(v1 + cc * 8); }
-          if (c >= 1) { mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1; }     // fc2[c-1] finished reading H
-          unsigned char* H = smem + OFF_H + hsel * 16384 + r * 16;
+          for (int cc = 0; cc < 4; ++cc) hv[cc] = relu_pack8(v + cc * 8);
+          const int hs = c & 3;                                           // hidden slot (4 x 16 KB over A|H)
+          if (c >= 4) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }   // fc2[c-4] finished reading it
+          unsigned char* H = smem + OFF_A + hs * 16384 + hsel * 8192 + r * 16;
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = hv[cc];
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = hv[cc];
           signal_ready();
           TR(0, 22);
         }
-        // block end: fc2[2] complete => x is final for this block, params/H/A reusable
-        mbar_wait_all(&bars[B_H], ph_h); ph_h ^= 1;
+        // block end: fc2[2..5] complete (slots 2, 3, 0, 1) => x is final for this block, A|H reusable
+#pragma unroll
+        for (int hs = 0; hs < 4; ++hs) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }
         tc_fence_after();
         TR(0, 23);
       }

@@ -280,16 +280,18 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
       pack_kmajor(w, wq.data(), 128, 0, 96, 64, 64); w += 96 * 64;              // slot: Wqkv' K half 1
       pack_kmajor(w, b[4], 32, 0, 128, 0, 32); w += 128 * 32;                   // slot: Wproj [128][32] ...
       pack_bias_tile(w, b[5], 128); w += 128 * 8;                               //       ... + proj bias tile
-      // MLP in 3 chunks of 128 hidden units; weight tiles are [128 x 64] K-major (4 MMA k-steps)
-      auto w1 = [&](int c) {                                                     // fc1' rows 128c.., K halves, + bias' tile
-        for (int kh = 0; kh < 2; ++kh) { pack_kmajor(w, w1f.data(), 128, c * 128, 128, kh * 64, 64); w += 128 * 64; }
-        pack_bias_tile(w, b1f.data() + c * 128, 128); w += 128 * 8;
+      // MLP in 6 chunks of 64 hidden units: fc1 chunk = [64 x 128] K-major (8 k-steps) + its bias' tile,
+      // fc2 chunk = [128 x 64] K-major (4 k-steps); the fc2 bias tile rides behind the first fc2 chunk
+      auto w1 = [&](int c) {
+        pack_kmajor(w, w1f.data(), 128, c * 64, 64, 0, 128); w += 64 * 128;
+        pack_bias_tile(w, b1f.data() + c * 64, 64); w += 64 * 8;
       };
-      auto w2 = [&](int c) {                                                     // fc2 K slices 128c + 64hh .. (+ fc2 bias tile once)
-        for (int hh = 0; hh < 2; ++hh) { pack_kmajor(w, b[10], 384, 0, 128, c * 128 + hh * 64, 64); w += 128 * 64; }
+      auto w2 = [&](int c) {
+        pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64;
         if (c == 0) { pack_bias_tile(w, b[11], 128); w += 128 * 8; }
       };
-      w1(0); w1(1); w2(0); w1(2); w2(1); w2(2);
+      w1(0);
+      for (int c = 0; c < 6; ++c) { if (c < 5) w1(c + 1); w2(c); }
       if ((size_t)(reinterpret_cast<unsigned char*>(w) - blk) != encoder_tc_block_bytes()) {
         set_error("internal: packed block is %zu bytes, kernel expects %zu", (size_t)(reinterpret_cast<unsigned char*>(w) - blk),
                   encoder_tc_block_bytes());
