@@ -18,7 +18,7 @@ NAMES = {1: "tile start", 2: "patch gather+signal", 3: "patch MMA wait", 10: "po
          11: "LN1+signal", 12: "qkv MMA wait", 13: "qkv epilogue+signal", 14: "S MMA wait", 15: "softmax+P+signal",
          16: "PV MMA wait", 17: "O read(+signal)", 18: "A_o signal", 19: "proj MMA wait", 20: "LN2+signal",
          21: "fc1/H wait", 22: "relu epilogue+signal", 23: "final fc2 waits", 30: "final LN + pool"}
-INAMES = {1: "wait_ready", 2: "weights FULL wait", 3: "MMAs issued+commit"}
+INAMES = {1: "ready signal received", 2: "weights in ring", 3: "MMAs issued+commit"}
 
 
 def decode(buf):
@@ -67,6 +67,22 @@ def main():
                 agg[(int(ids[i - 1]), int(ids[i]))].append(int(d[i - 1]))
             for k, v in sorted(agg.items()):
                 out.append(f"   {names.get(k[0], k[0])!s:>24} -> {names.get(k[1], k[1])!s:<24} n={len(v):4d} mean {np.mean(v):8.0f}  min {np.min(v):6d}  max {np.max(v):6d}  sum {np.sum(v):9d}")
+    # merged absolute timeline of one block (compute thread 0 + issuer), cycles relative to the block start
+    bufs = []
+    for which in (0, 1):
+        buf = np.zeros(4096, dtype=np.int64)
+        N.check(lib.uitk_debug_read_trace(buf.ctypes.data, which, 4096), "read_trace")
+        bufs.append(decode(buf))
+    ids0, clk0 = bufs[0]
+    starts = np.where(ids0 == 10)[0]
+    if len(starts) > 7:
+        t_a, t_b = clk0[starts[5]], clk0[starts[6]]
+        ev = [(int(c - t_a), "C", NAMES.get(int(i), str(int(i)))) for i, c in zip(ids0, clk0) if t_a <= c <= t_b]
+        ids1, clk1 = bufs[1]
+        ev += [(int(c - t_a), "  I", INAMES.get(int(i), str(int(i)))) for i, c in zip(ids1, clk1) if t_a - 500 <= c <= t_b]
+        out.append("== merged timeline of block 5 (cycles from block start; C = compute thread 0, I = MMA issuer)")
+        for t, w, n in sorted(ev):
+            out.append(f"   {t:7d} {w} {n}")
     txt = "\n".join(out)
     print(txt)
     os.makedirs("gpurun_out", exist_ok=True)

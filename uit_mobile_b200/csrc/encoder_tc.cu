@@ -273,10 +273,12 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           ring_load(wb, kQkvHalfBytes);
           ring_load(wb, kProjBytes + kBiasTile);
           ring_load(wb, kTile + kFc1BiasBytes);                                                      // fc1[0]
-          for (int c = 0; c < 6; ++c) {
+          ring_load(wb, kTile + kFc1BiasBytes);                                                      // fc1[1]
+          for (int c = 1; c < 6; ++c) {
             if (c < 5) ring_load(wb, kTile + kFc1BiasBytes);                                          // fc1[c+1]
-            ring_load(wb, kTile + (c == 0 ? kBiasTile : 0u));                                         // fc2[c] (+ fc2 bias once)
+            ring_load(wb, kTile + (c == 1 ? kBiasTile : 0u));                                         // fc2[c-1] (+ fc2 bias once)
           }
+          ring_load(wb, kTile);                                                                      // fc2[5]
         }
       }
     }
@@ -392,14 +394,24 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             TR(1, 3);
             if (++cslot == kSlots) { cslot = 0; cphase ^= 1; }
           };
-          fc1();
-          for (int c = 0; c < 6; ++c) {
-            wait_ready();                                                     // accumulator drained into registers
-            if (c < 5) fc1();                                                 // fc1[c+1] runs while the ReLU epilogue of chunk c does
-            wait_ready();                                                     // H slot c & 3 written
-            mma_from_ring(tmem, sA + (c & 3) * 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // fc2[c]: x += H_c W2_c^T (+ b2 once)
+          // The issue of an MMA group blocks this warp for about as long as the group executes, so fc2 runs ONE CHUNK
+          // LATE: on "accumulator c drained" the issuer sends fc1[c+1] and fc2[c-1] (whose hidden slot was signalled long
+          // ago) in one go and is back waiting before drained(c+1) arrives; the hidden ring is 4 deep, so nobody waits.
+          auto fc2 = [&](int c) {
+            mma_from_ring(tmem, sA + (c & 3) * 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // x += H_c W2_c^T (+ b2 once)
             commit(&bars[B_H + (c & 3)]);
+          };
+          fc1();                                                              // fc1[0]
+          wait_ready();                                                       // accumulator 0 drained into registers
+          fc1();                                                              // fc1[1] runs while the ReLU epilogue of chunk 0 does
+          for (int c = 1; c < 6; ++c) {
+            wait_ready();                                                     // hidden slot of chunk c-1 written
+            wait_ready();                                                     // accumulator c drained
+            if (c < 5) fc1();                                                 // fc1[c+1]
+            fc2(c - 1);
           }
+          wait_ready();                                                       // hidden slot of chunk 5 written
+          fc2(5);
         }
       }
     }

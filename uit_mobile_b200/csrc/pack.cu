@@ -290,8 +290,9 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
         pack_kmajor(w, b[10], 384, 0, 128, c * 64, 64); w += 128 * 64;
         if (c == 0) { pack_bias_tile(w, b[11], 128); w += 128 * 8; }
       };
-      w1(0);
-      for (int c = 0; c < 6; ++c) { if (c < 5) w1(c + 1); w2(c); }
+      w1(0); w1(1);                                                              // issue order of csrc/encoder_tc.cu: fc2 one chunk late
+      for (int c = 1; c < 6; ++c) { if (c < 5) w1(c + 1); w2(c - 1); }
+      w2(5);
       if ((size_t)(reinterpret_cast<unsigned char*>(w) - blk) != encoder_tc_block_bytes()) {
         set_error("internal: packed block is %zu bytes, kernel expects %zu", (size_t)(reinterpret_cast<unsigned char*>(w) - blk),
                   encoder_tc_block_bytes());
