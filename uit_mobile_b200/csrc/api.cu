@@ -78,7 +78,7 @@ static int encoder_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, i
 size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
   int64_t rows = 0;
   if (encoder_geometry(cfg, B, T, target_length, &rows) != UITK_OK) return 0;
-  if (cfg->precision == UITK_PREC_BF16)
+  if (cfg->precision == UITK_PREC_BF16 && time_patches_for(T, target_length) == 6)       // 24 tokens: tensor-core megakernel
     return encoder_tc_workspace_bytes(B * crops_for(T, target_length), rows) + 256;
   return encoder_fp32_workspace_bytes(rows) + 256;
 }

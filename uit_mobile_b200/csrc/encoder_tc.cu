@@ -33,7 +33,7 @@ constexpr int kCompute = 256;
 constexpr uint32_t kTile = 16384;                     // one [128 x 64] bf16 K-major weight tile = 4 MMA k-steps
 constexpr uint32_t kBiasTile = 128 * 16;              // [128 x 8] bf16 bias tile (pack.cu: pack_bias_tile)
 constexpr uint32_t kSlot = kTile + kBiasTile;         // ring slot: a weight tile and, for some, the bias tile behind it
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;
 constexpr uint32_t kQkvHalfBytes = 96 * 64 * 2;       // Wqkv, one K half: 12288
 constexpr uint32_t kQkvBiasBytes = 96 * 16;           // 1536
 constexpr uint32_t kProjBytes = 128 * 32 * 2;         // 8192
@@ -42,35 +42,38 @@ constexpr uint32_t kFc1BiasBytes = 64 * 16;           // bias tile of one 64-col
 constexpr uint32_t kBlockBytes = 2 * kQkvHalfBytes + kQkvBiasBytes + kProjBytes + kBiasTile + 6 * (kTile + kFc1BiasBytes) + 6 * kTile + kBiasTile;
 constexpr uint32_t kPatchBytes = 4 * kTile;           // 4 K-quarters of the patch weight
 
-// shared memory map (bytes); one CTA uses 108.3 KB so that two fit on an SM
-constexpr uint32_t OFF_A = 0;                      // 32 KB: A operand (LN output) | patch k 0..127 | attention scratch
-constexpr uint32_t OFF_H = 32768;                  // 2 x 16 KB hidden chunks     | patch k 128..255 | attention scratch
+// shared memory map (bytes); one CTA uses 110.3 KB so that two fit on an SM
+//   [0, 48 KB)   three 16 KB operand slots.  Attention phase: slot 0|1 = A (LayerNorm-1 output, 32 KB), later A_o + Q + K over
+//                it; slot 2 = V^T.  MLP phase: 3-deep ring of hidden chunks (ReLU output, A operand of fc2).  Patch embed: the
+//                [128 x 128] bf16 operand of one K half (32 KB).
+//   [48 KB, ..)  weight ring: kSlots x 18 KB, filled by the producer warp with 1-D bulk copies in consumption order
+constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_AO = OFF_A;                 // 8 KB attention output operand [128 x 32]
-constexpr uint32_t OFF_QKV = OFF_A + 8192;         // [128][100] fp32 + 16 B per clip = <= 51712 B (ends inside H)
-// tensor-core attention operands (tokens == 24), all inside A|H which are idle between the qkv and proj GEMMs
 constexpr uint32_t OFF_Q = OFF_A + 8192;           // Q_h  [128 x 16] bf16 K-major, head h at + h*4096
 constexpr uint32_t OFF_K = OFF_A + 16384;          // K_h  [128 x 16] (B operand: N = key row)
 // V_h^T [16 x 128] (B operand: N = d, K = key row).  k-groups are 272 B apart (LBO is free in the descriptor): the 4 key
 // groups a warp's 2-byte transposing stores hit then fall into distinct banks.  Head h at + h * kVtHead.
-constexpr uint32_t OFF_VT = OFF_H;
+constexpr uint32_t OFF_VT = OFF_A + 32768;
 constexpr uint32_t kVtLbo = 272, kVtHead = 16 * kVtLbo;
+constexpr int kHSlots = 3;                         // hidden-chunk slots (16 KB each) at OFF_A + s * 16384
 // P_h (softmax probabilities, block diagonal) never touches shared memory: it is written to TENSOR MEMORY (accumulator
 // columns 0..63, packed bf16 pairs, over the dead S_h) and is the TMEM A operand of the P V product; O_h lands in
 // accumulator columns 64..79.
 constexpr uint32_t kColP = 0, kColO = 64;
 // MLP phase: fc1 chunk accumulator (64 fp32 columns) and the LayerNorm-2 output as packed-bf16 TMEM A operand (64 columns)
 constexpr uint32_t kColFc1 = 0, kColLn2 = 64;
-constexpr uint32_t OFF_RING = 65536;               // 2 x 16 KB
+constexpr uint32_t OFF_RING = kHSlots * 16384;
 // constant MMA operands: k-group of (1, 1, 1, 0, ..) rows = the A operand of every bias k-step, then 2 KB of zeros that
 // serve as the second k-group of both the ones operand and every bias tile (their LBO points here: it must lie ABOVE the ring)
 constexpr uint32_t OFF_CONST = OFF_RING + kSlots * kSlot;
 constexpr uint32_t OFF_PART = OFF_CONST + 4096;             // 2 x 512 floats
 constexpr uint32_t OFF_BAR = OFF_PART + 2 * 512 * 4;   // two alternating buffers of [2][128] float2 partial sums
 constexpr uint32_t kSmemBytes = OFF_BAR + 256;
-constexpr int QKV_LD = 100;   // 400-B rows: float4-aligned, and 8 consecutive rows hit 8 distinct 16-B bank groups
+static_assert(kSmemBytes <= 115712, "two CTAs per SM need <= 113 KB of dynamic shared memory each");
 constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = 2, B_ACC = 4, B_X = 5, B_FC1 = 6, B_H = 7 /* 4 hidden slots */, B_COUNT = 11 };
+enum { B_FULLW = 0, B_EMPTYW = kSlots, B_ACC = 2 * kSlots, B_X, B_FC1, B_H /* kHSlots hidden slots */, B_COUNT = B_H + kHSlots };
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
@@ -82,7 +85,6 @@ struct TcParams {
   int RR, G, num_tiles, depth;
   float* pooled;   // [RR][128]
   float* dbg_x;    // optional [RR*tokens][128]: residual stream after the last block (pre final LN)
-  int tc_attn;     // 1: attention GEMMs on tcgen05 (needs tokens == 24); 0: CUDA-core attention
 };
 
 // Optional in-kernel timeline (build with -DUITK_TRACE): thread 0 of CTA 0 and its MMA-issuer thread stamp
@@ -291,12 +293,11 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     // It waits for (a) the "operand ready" signal of the 256 compute threads (alternating mbarriers) and (b) the weight
     // chunk in the ring; the compute warps never block on weights, only on the completion barriers (ACC / X / FC1 / H).
     {
-      const uint32_t sA = smem_u32(smem + OFF_A), sH = smem_u32(smem + OFF_H), sRing = smem_u32(smem + OFF_RING);
+      const uint32_t sA = smem_u32(smem + OFF_A), sRing = smem_u32(smem + OFF_RING);
       const uint32_t sOnes = smem_u32(smem + OFF_CONST), sZero = sOnes + 2048;
       const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sVT = smem_u32(smem + OFF_VT);
       constexpr uint32_t ID128 = make_idesc_bf16(128, 128), ID96 = make_idesc_bf16(128, 96), ID64 = make_idesc_bf16(128, 64);
       constexpr uint32_t ID16 = make_idesc_bf16(128, 16);
-      const bool tc_attn = p.tc_attn != 0;
       uint32_t cslot = 0, cphase = 0, sig = 0;
 #ifdef UITK_TRACE
       const bool trace_on = blockIdx.x == 0 && lane == 0;
@@ -346,15 +347,17 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       using K4 = std::integral_constant<int, 4>;
       using K8 = std::integral_constant<int, 8>;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        wait_ready();                                                         // patch operand gathered
-        for (int c = 0; c < 4; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, K4{}, c > 0);
-        commit(&bars[B_ACC]);
+        for (int half = 0; half < 2; ++half) {                                // patch embed, one K half (128 of 256) at a time
+          wait_ready();                                                       // operand half gathered into A
+          for (int c = 0; c < 2; ++c) mma_from_ring(tmem, sA + c * 16384, ID128, 2048, K4{}, half + c > 0);
+          commit(&bars[B_ACC]);
+        }
         for (int blk = 0; blk < p.depth; ++blk) {
           wait_ready();                                                       // LN1 output in A
           mma_from_ring(tmem + 128, sA, ID96, 1536, K4{}, false, kQkvHalfBytes);
           mma_from_ring(tmem + 128, sA + 16384, ID96, 1536, K4{}, true);
           commit(&bars[B_ACC]);
-          if (tc_attn) {                                                      // attention GEMMs (no weights involved)
+          {                                                                   // attention GEMMs (no weights involved)
             for (int h = 0; h < 2; ++h) {
               wait_ready();                                                   // Q/K/V^T operands written (h=0) / ACC drained (h=1)
               if (elect_one()) {
@@ -396,10 +399,10 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           };
           // The issue of an MMA group blocks this warp for about as long as the group executes, so fc2 runs ONE CHUNK
           // LATE: on "accumulator c drained" the issuer sends fc1[c+1] and fc2[c-1] (whose hidden slot was signalled long
-          // ago) in one go and is back waiting before drained(c+1) arrives; the hidden ring is 4 deep, so nobody waits.
+          // ago) in one go and is back waiting before drained(c+1) arrives; the hidden ring is 3 deep, so nobody waits.
           auto fc2 = [&](int c) {
-            mma_from_ring(tmem, sA + (c & 3) * 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // x += H_c W2_c^T (+ b2 once)
-            commit(&bars[B_H + (c & 3)]);
+            mma_from_ring(tmem, sA + (c % kHSlots) * 16384, ID128, 2048, K4{}, true, c == 0 ? (int)kTile : -1);   // x += H_c W2_c^T (+ b2 once)
+            commit(&bars[B_H + (c % kHSlots)]);
           };
           fc1();                                                              // fc1[0]
           wait_ready();                                                       // accumulator 0 drained into registers
@@ -452,44 +455,52 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       const int rows_valid = g_cnt * tokens;
       TR(0, 1);
 
-      // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A[128 x 256] over A|H ----------------
-      for (int i = tid; i < (128 - rows_valid) * 32; i += kCompute) {      // zero the padding rows
-        const int rz = rows_valid + i / 32, k8 = i % 32;
-        *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
-      }
-      // each warp handles one clip-crop's 64 mel rows at a time (8 rows = 24 coalesced loads in flight per lane)
-      for (int g = 0; g < g_cnt; ++g) {
-        const int rr = rr0 + g;
-        const int b = rr / p.crops, c = rr - b * p.crops;
-        int start = 0;
-        if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
-        const float* src0 = p.db + ((size_t)b * 64 + warp * 8) * p.T + start;     // this warp: mel rows warp*8 .. warp*8+7
-        float val[8][3];
+      // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A, one K half [128 x 128] at a time ----------------
+      // k = df * 16 + dt (df = mel & 15): K half h holds df in [8h, 8h + 8).  Warp w gathers token row f = w >> 1 and the
+      // 4 mel rows 16 f + 8 h + 4 (w & 1) + u of every clip-crop of the tile (12 coalesced loads in flight per lane).
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {                                                   // MMAs of half 0 have read A
+          mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
+        }
+        for (int i = tid; i < (128 - rows_valid) * 16; i += kCompute) {      // zero the padding rows
+          const int rz = rows_valid + i / 16, k8 = i % 16;
+          *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
+        }
+        const int f = warp >> 1, dfl0 = 4 * (warp & 1);
+        for (int g = 0; g < g_cnt; ++g) {
+          const int rr = rr0 + g;
+          const int b = rr / p.crops, c = rr - b * p.crops;
+          int start = 0;
+          if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
+          const int mel0 = 16 * f + 8 * half + dfl0;
+          const float* src0 = p.db + ((size_t)b * 64 + mel0) * p.T + start;
+          float val[4][3];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int tt = lane + 32 * j;
-            val[u][j] = tt < 16 * t_n ? __ldg(src0 + (size_t)u * p.T + tt) : 0.f;
-          }
+            for (int j = 0; j < 3; ++j) {
+              const int tt = lane + 32 * j;
+              val[u][j] = tt < 16 * t_n ? __ldg(src0 + (size_t)u * p.T + tt) : 0.f;
+            }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int mel = warp * 8 + u;
-          const float sc = __ldg(p.bn_scale + mel), sh = __ldg(p.bn_shift + mel);
-          const int rbase = g * tokens + (mel >> 4) * t_n;
+          for (int u = 0; u < 4; ++u) {
+            const float sc = __ldg(p.bn_scale + mel0 + u), sh = __ldg(p.bn_shift + mel0 + u);
+            const int rbase = g * tokens + f * t_n;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int tt = lane + 32 * j;
-            if (tt < 16 * t_n) {
-              const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
-              const int k = (mel & 15) * 16 + (tt & 15);
-              const int rrow = rbase + (tt >> 4);
-              *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
+            for (int j = 0; j < 3; ++j) {
+              const int tt = lane + 32 * j;
+              if (tt < 16 * t_n) {
+                const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
+                const int k = (dfl0 + u) * 16 + (tt & 15);                 // k within the half
+                const int rrow = rbase + (tt >> 4);
+                *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
+              }
             }
           }
         }
+        signal_ready();
       }
-      signal_ready();
       TR(0, 2);
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
         tc_fence_after();
         TR(0, 12);
-        if (p.tc_attn) {
+        {
           // ---------- tensor-core attention: S_h = Q_h K_h^T and O_h = P_h V_h on tcgen05, softmax straight from TMEM ----------
           const bool valid = r < rows_valid;
           const int g = valid ? r / 24 : 0;
@@ -640,85 +651,6 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             if (h == 0) signal_drained();                                 // ACC drained: S_1 may overwrite it
             TR(0, 17);
           }
-        } else {
-        {   // qkv (+bias) -> fp32 scratch [128][100]
-          // rows of different clips are 24*400 B apart = the same banks: a 16-B pad per clip lets the two clips a warp
-          // straddles be served in one wavefront when the attention threads broadcast-read k/v rows
-          float* dstq = reinterpret_cast<float*>(smem + OFF_QKV) + r * QKV_LD + (r / tokens) * 4 + hsel * 48;
-          float v[32];
-          tmem_ld32(tacc + hsel * 48, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dstq + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          float w[16];
-          tmem_ld16(tacc + hsel * 48 + 32, w);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dstq + 32 + i) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
-        }
-        tc_fence_before();
-        bar_compute();
-        {   // attention: thread = (row, head); softmax((q k^T) * 0.125) v   (uit.py:115-119)
-          const float* qkv = reinterpret_cast<const float*>(smem + OFF_QKV);
-          const int ar = tid & 127, h = tid >> 7;
-          float2 o2[8];
-#pragma unroll
-          for (int d = 0; d < 8; ++d) o2[d] = make_float2(0.f, 0.f);
-          if (ar < rows_valid) {
-            const int clip = ar / tokens;
-            const int base = clip * tokens;
-            const float* qkv_c = qkv + clip * 4;              // per-clip pad (see the qkv epilogue)
-            float qv[16];
-#pragma unroll
-            for (int d = 0; d < 16; d += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(qkv_c + ar * QKV_LD + h * 16 + d);
-              qv[d] = t4.x; qv[d + 1] = t4.y; qv[d + 2] = t4.z; qv[d + 3] = t4.w;
-            }
-            float sc[UITK_MAX_TOKENS];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
-              float a = 0.f;
-              if (j < tokens) {
-                const float4* kj = reinterpret_cast<const float4*>(qkv_c + (base + j) * QKV_LD + 32 + h * 16);
-                float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                  const float4 k4 = kj[d];
-                  a2 = fma2(make_float2(qv[4 * d], qv[4 * d + 1]), make_float2(k4.x, k4.y), a2);
-                  b2 = fma2(make_float2(qv[4 * d + 2], qv[4 * d + 3]), make_float2(k4.z, k4.w), b2);
-                }
-                a = ((a2.x + a2.y) + (b2.x + b2.y)) * 0.125f;
-                mx = fmaxf(mx, a);
-              }
-              sc[j] = a;
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
-              sc[j] = j < tokens ? __expf(sc[j] - mx) : 0.f;
-              sum += sc[j];
-            }
-            const float inv = 1.f / sum;
-#pragma unroll
-            for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
-              if (j < tokens) {
-                const float pj = sc[j] * inv;
-                const float2 pp = make_float2(pj, pj);
-                const float4* vj = reinterpret_cast<const float4*>(qkv_c + (base + j) * QKV_LD + 64 + h * 16);
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                  const float4 v4 = vj[d];
-                  o2[2 * d] = fma2(pp, make_float2(v4.x, v4.y), o2[2 * d]);
-                  o2[2 * d + 1] = fma2(pp, make_float2(v4.z, v4.w), o2[2 * d + 1]);
-                }
-              }
-            }
-          }
-          const float* out = reinterpret_cast<const float*>(o2);
-          *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 0) * 2048 + ar * 16) = pack8_bf16(out);
-          *reinterpret_cast<uint4*>(smem + OFF_AO + (h * 2 + 1) * 2048 + ar * 16) = pack8_bf16(out + 8);
-        }
         }
         signal_ready();
         TR(0, 18);
@@ -743,58 +675,63 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           uint4 hv[4];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) hv[cc] = relu_pack8(v + cc * 8);
-          const int hs = c & 3;                                           // hidden slot (4 x 16 KB over A|H)
-          if (c >= 4) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }   // fc2[c-4] finished reading it
+          const int hs = c % kHSlots;                                     // hidden slot
+          if (c >= kHSlots) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }   // fc2[c-4] finished reading it
           unsigned char* H = smem + OFF_A + hs * 16384 + hsel * 8192 + r * 16;
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(H + cc * 2048) = hv[cc];
           signal_ready();
           TR(0, 22);
         }
-        // block end: fc2[2..5] complete (slots 2, 3, 0, 1) => x is final for this block, A|H reusable
+        // block end: fc2[3..5] complete (slots 0, 1, 2) => x is final for this block, the operand slots are reusable
 #pragma unroll
-        for (int hs = 0; hs < 4; ++hs) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }
+        for (int hs = 0; hs < kHSlots; ++hs) { mbar_wait_all(&bars[B_H + hs], (ph_h >> hs) & 1); ph_h ^= 1u << hs; }
         tc_fence_after();
         TR(0, 23);
       }
 
       // ---------------- final LayerNorm (eps 1e-6) + token mean -> pooled[rr][128] ----------------
+      // The affine part commutes with the token mean: pooled = gamma * mean_t((x - mu) rstd) + beta.  The normalised rows go
+      // through a [128][64] fp32 staging tile (32 KB, 16-B chunks XOR-swizzled by row), one column half per pass.
       {
-        float* Y = reinterpret_cast<float*>(smem + OFF_A);      // [128][128] fp32 over A|H, 16-B chunks XOR-swizzled by row
+        float* Y = reinterpret_cast<float*>(smem + OFF_A);
         float mean, rstd;
         row_stats(tx, hsel, r, 1e-6f, part, mean, rstd);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float v[32];
-          tmem_ld32(tx + hsel * 64 + j * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int k = hsel * 64 + j * 32 + i;
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.norm_b + k));
-            const float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
-            if (p.dbg_x != nullptr && r < rows_valid)
-              *reinterpret_cast<float4*>(p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + k) = make_float4(x0, x1, x2, x3);
-            float4 o;
-            o.x = (x0 - mean) * rstd * g4.x + b4.x; o.y = (x1 - mean) * rstd * g4.y + b4.y;
-            o.z = (x2 - mean) * rstd * g4.z + b4.z; o.w = (x3 - mean) * rstd * g4.w + b4.w;
-            *reinterpret_cast<float4*>(&Y[r * 128 + ((((k >> 2) ^ (r & 7)) << 2))]) = o;
-          }
-        }
-        tc_fence_before();
-        bar_compute();
-        const int col = tid & 127;
         const float invn = 1.f / (float)tokens;
-        for (int g = tid >> 7; g < g_cnt; g += 2) {
-          float acc = 0.f;
-          for (int t = 0; t < tokens; ++t) {
-            const int row = g * tokens + t;
-            acc += Y[row * 128 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3))];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          if (hsel == pass) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              float v[32];
+              tmem_ld32(tx + hsel * 64 + j * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const int kl = j * 32 + i;                                  // column within the half
+                if (p.dbg_x != nullptr && r < rows_valid)
+                  *reinterpret_cast<float4*>(p.dbg_x + ((size_t)rr0 * tokens + r) * 128 + hsel * 64 + kl) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                float4 o;
+                o.x = (v[i] - mean) * rstd; o.y = (v[i + 1] - mean) * rstd;
+                o.z = (v[i + 2] - mean) * rstd; o.w = (v[i + 3] - mean) * rstd;
+                *reinterpret_cast<float4*>(&Y[r * 64 + ((((kl >> 2) ^ (r & 7)) << 2))]) = o;
+              }
+            }
           }
-          p.pooled[(size_t)(rr0 + g) * 128 + col] = acc * invn;
+          tc_fence_before();
+          bar_compute();
+          const int col = tid & 63, k = pass * 64 + col;
+          const float gam = __ldg(p.norm_w + k), bet = __ldg(p.norm_b + k);
+          for (int g = tid >> 6; g < g_cnt; g += 4) {
+            float acc = 0.f;
+            for (int t = 0; t < tokens; ++t) {
+              const int row = g * tokens + t;
+              acc += Y[row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3))];
+            }
+            p.pooled[(size_t)(rr0 + g) * 128 + k] = fmaf(gam, acc * invn, bet);
+          }
+          bar_compute();     // Y is free again (next pass / next tile's gather)
         }
-        bar_compute();     // Y (aliases A|H) is free again before the next tile's gather
         TR(0, 30);
       }
     }
@@ -840,6 +777,10 @@ int run_encoder_tc(const EncoderArgs& a) {
   const int t_n = time_patches_for(a.T, a.target_length);
   const int tokens = 4 * t_n;
   const int64_t RR = a.B * crops;
+  // The megakernel is built for the model's native geometry (24 tokens per crop = 5 crops per 128-row tile; every clip of
+  // >= 1 s).  Shorter clips (4..20 tokens) take the unfused fp32 CUDA-core kernels: a GPU path chosen by shape, with more
+  // precision than asked for; uitk_encoder_workspace_bytes() accounts for it.
+  if (tokens != 24) return run_encoder_fp32(a);
   UITK_REQUIRE(RR * tokens < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call; chunk the batch");
   UITK_REQUIRE(t_n <= cfg.grid_t, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
   const EncoderLayout lay = make_encoder_layout(cfg.depth, cfg.outputdim, cfg.grid_t);
@@ -863,7 +804,6 @@ int run_encoder_tc(const EncoderArgs& a) {
   p.RR = (int)RR; p.G = 128 / tokens; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;
   p.pooled = pooled;
   p.dbg_x = (a.debug_taps & 1) ? dbg_x : nullptr;
-  p.tc_attn = (tokens == 24 && !(a.debug_taps & 2)) ? 1 : 0;     // debug bit 1 forces the CUDA-core attention
 
   int dev = 0, sms = 0;
   UITK_CHECK_CUDA(cudaGetDevice(&dev));
