@@ -1,21 +1,35 @@
 // Tensor-core encoder (UITK_PREC_BF16): ONE persistent megakernel runs patch embed + every transformer block for a
 // tile of 128 token rows (5 clip-crops x 24 tokens) per CTA, with tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
-// TWO CTAs are resident per SM (<= 112 regs/thread, 108 KB SMEM, 256 TMEM columns each) so that one CTA's
+// TWO CTAs are resident per SM (96 regs/thread, 110 KB SMEM, 256 TMEM columns each) so that one CTA's
 // LayerNorm / softmax / ReLU work on the CUDA cores overlaps the other CTA's MMAs and weight streaming.
 //
 //   * the fp32 residual stream x[128 x 128] never leaves TENSOR MEMORY (columns 0..127): the proj and fc2 GEMMs
-//     accumulate straight onto it (the residual add is the MMA's accumulate), their biases are deferred into a
-//     running per-column bias vector that the next LayerNorm read adds (packed at load time);
-//   * GEMM accumulators (qkv: 96 columns; fc1 hidden: 2 x 64-column chunks, double buffered) live in columns 128..255;
-//   * A operands (LayerNorm output, attention output, ReLU hidden) are produced by the CUDA cores straight from
-//     tcgen05.ld registers into K-major core-matrix shared-memory tiles (thread == row, so every 16-byte store of a
-//     warp is contiguous: no bank conflicts, no swizzle needed);
-//   * weights are pre-packed on the host in exactly that shared-memory layout and in consumption order, so a
-//     producer warp streams them L2 -> SMEM with plain 1-D cp.async.bulk copies through a 2 x 16 KB mbarrier ring
-//     (full/empty, slots released by tcgen05.commit); the MLP runs as 6 hidden chunks of 64 columns with fc1 of
-//     chunk c+2 issued behind fc2 of chunk c, so ReLU epilogues overlap MMAs;
-//   * attention (2 heads x 24 x 24 x 16 per clip) stays on the CUDA cores, one thread per (row, head), fp32 softmax.
+//     accumulate straight onto it (the residual add is the MMA's accumulate);
+//   * every Linear bias is added by the tensor core: a [N x 8] bf16 "bias tile" (hi/mid/lo split of the fp32 bias,
+//     pack.cu) rides behind the weights in the ring and one extra k-step multiplies it with a constant ones operand.
+//     The CUDA cores never load or add a parameter: LayerNorm affines are folded into the next Linear at pack time;
+//   * accumulators / TMEM operands live in columns 128..255: qkv (96) -> S_h (128) -> P_h (packed bf16, 64) + O_h (16)
+//     in the attention phase; LayerNorm-2 output (packed bf16, 64) + fc1 chunk (64) in the MLP phase.  P_h and the
+//     LayerNorm-2 output are TMEM A operands (TS-mode tcgen05.mma): no shared-memory store, read or proxy fence, and
+//     the k-step runs at the tensor-core floor (an SS-mode k-step at N <= 128 is bound by the 128 B/cycle of SMEM);
+//   * the remaining A operands (LayerNorm-1 output, Q/K/V^T, attention output, ReLU hidden chunks) are produced by the
+//     CUDA cores straight from tcgen05.ld registers into K-major core-matrix shared-memory tiles (thread == row, so
+//     every 16-byte store of a warp is contiguous: no bank conflicts, no swizzle needed);
+//   * weights are pre-packed on the host in exactly that shared-memory layout and in consumption order, so a producer
+//     warp streams them L2 -> SMEM with plain 1-D cp.async.bulk copies through a 3 x 18 KB mbarrier ring (full/empty,
+//     slots released by tcgen05.commit);
+//   * one MMA-issuer WARP (all 32 lanes run the warp-uniform issue code, one elected lane executes the tcgen05
+//     instructions, so descriptors stay in uniform registers and UTCHMMA goes out back to back); the compute warps
+//     hand operands over through non-blocking named-barrier arrivals and only ever wait on MMA-completion mbarriers;
+//   * the MLP runs as 6 hidden chunks of 64 columns: "accumulator drained" is signalled as soon as the chunk is in
+//     registers so fc1[c+1] runs under the ReLU epilogue of chunk c, fc2 is issued one chunk late together with the
+//     next fc1 (the issue of a group blocks the issuer for about its execution time), hidden chunks cycle through a
+//     3-deep ring;
+//   * attention on the tensor cores: S_h = Q_h K_h^T for the whole tile (N = 128), fp32 softmax of each row's own 24
+//     keys straight from TMEM, O_h = P_h V_h with the block-diagonal P_h in TMEM.
 // LayerNorm, softmax, residual and all accumulation are fp32; only GEMM operands are rounded to bf16.
+// Measured design inputs (scripts/microbench/tc_micro.cu, profiles/r1_tc_microbench.txt): SS k-step = max(~39, N/2)
+// cycles, TS k-step = max(~11, N/2); fence.proxy.async ~120-140; mbarrier wake ~140-150; named barrier ~30.
 // Reference semantics: models/uit.py:379-396 (features), 89-122 (attention), 181-248 (MLP, block).
 #include <type_traits>
 
