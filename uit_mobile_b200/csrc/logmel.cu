@@ -4,12 +4,15 @@
 // (models/uit.py:298-308, 455; torchaudio functional.spectrogram :123-144, MelScale :407-419, amplitude_to_DB :390).
 // The batch-global top-dB clamp (Q2) is NOT applied here: the kernel only tracks the global maximum.
 //
-// One CTA = one chunk of up to 112 frames of one clip, processed as 7 rounds of 16 frames.  A frame's 512-point
-// real DFT is computed as a 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) by 16 threads (half a warp), each
-// holding 16 complex points in registers: radix-16 pass over registers, W256 twiddle, 16x16 transpose through
-// shared memory (warp-synchronous, padded rows), second radix-16 pass, real-FFT unpack, |X|^2, sparse mel
-// (<=2 non-zero filters per bin -> packed ranges), dB.  HBM sees every sample once (frames overlap 3.2x; the
-// overlap is absorbed by the staging buffer / L1) and every output once: 4*L + 4*64*T algorithmic bytes/clip.
+// The B * T frames of the batch are one flat list cut into rounds of 16 consecutive frames (a round may straddle two
+// clips, so T = 101 wastes no frame slot); one CTA = 7 consecutive rounds, 3 CTAs per SM (75.9 KB of shared memory each).
+// A frame's 512-point real DFT is computed as a
+// 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) by 16 threads (half a warp), each holding 16 complex points in
+// registers: radix-16 pass over registers, W256 twiddle, 16x16 transpose through shared memory (warp-synchronous, padded
+// rows), second radix-16 pass, real-FFT unpack, |X|^2, sparse mel (<=2 non-zero filters per bin -> packed ranges), dB.
+// The samples of round r+1 are staged with 16-byte cp.async while round r computes.  HBM sees every sample once (frames
+// overlap 3.2x; the overlap is absorbed by the staging buffer / L1) and every output once: 4*L + 4*64*T algorithmic
+// bytes/clip.
 #include "tc_ptx.cuh"
 #include "uitk_common.cuh"
 
@@ -19,9 +22,11 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kFramesPerRound = 16;
-constexpr int kRounds = 7;
-constexpr int kChunk = kFramesPerRound * kRounds;                              // 112 frames / CTA
-constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT;  // 2912
+constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT;  // 2912: 16 frames of ONE clip
+// A round that straddles a clip boundary stages two sample ranges back to back: the second clip's first frame starts
+// where the first clip's last frame ends, i.e. every slot of the second clip is shifted by n_fft - hop = 352 samples.
+constexpr int kStraddleShift = UITK_N_FFT - UITK_HOP;                            // 352
+constexpr int kStageFloats = kSamplesPerRound + kStraddleShift;                  // 3264
 constexpr int kExStride = 280;   // float2 per frame group: 16 x 17 used; 560 words = 16 mod 32 so that the two
                                  // frame groups of a warp use complementary banks for 32-bit accesses
 
@@ -83,7 +88,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 struct SmemLayout {
   float window[512];
   int mel_lo[64], mel_iters[4], mel_qoff[4];
-  float x[2][kSamplesPerRound];      // double buffered: cp.async stages round r+1 while round r computes
+  float x[2][kStageFloats];          // double buffered: cp.async stages round r+1 while round r computes
   float2 ex[kFramesPerRound * kExStride];
   float out[64 * 17];
   float red[16];
@@ -93,9 +98,46 @@ struct SmemLayout {
 // TIn = float (the reference's input contract) or int16_t (PCM ingest: x = pcm / 32768, dataset.py:44-46 /
 // torchaudio.load normalisation; the 2^-15 scale is folded into the window, which is exact, so both instantiations
 // produce bit-identical results for the same audio).
+// Where the 16 frame slots of round r come from.  straddle == 1 (T >= 16): slots are 16 consecutive frames of the flat
+// list, nA of them in clip cA (frames tA ..) and the rest in clip cA + 1 (frames 0 ..).  Otherwise rounds never cross a
+// clip (ceil(T / 16) rounds per clip, dead slots in the last one).
+struct Round {
+  long long cA;     // first clip
+  int tA, nA, nB;   // first frame in cA, live slots in cA, live slots in cA + 1
+};
+// (clip, first frame) of a round; stepped from round to round without divisions (one 64-bit division per CTA)
+struct RoundPos {
+  long long c;
+  int t;
+};
+__device__ __forceinline__ RoundPos round_pos(long long r, int T, int straddle, int rounds_per_clip) {
+  RoundPos P;
+  if (straddle) {
+    const long long F0 = r * kFramesPerRound;
+    P.c = F0 / T;
+    P.t = (int)(F0 - P.c * T);
+  } else {
+    P.c = r / rounds_per_clip;
+    P.t = (int)(r - P.c * rounds_per_clip) * kFramesPerRound;
+  }
+  return P;
+}
+__device__ __forceinline__ RoundPos next_pos(RoundPos P, int T, int straddle) {
+  P.t += kFramesPerRound;
+  if (P.t >= T) { P.t = straddle ? P.t - T : 0; ++P.c; }      // T >= 16 in straddle mode: at most one wrap
+  return P;
+}
+__device__ __forceinline__ Round round_at(RoundPos P, int T, long long B, int straddle) {
+  Round R;
+  R.cA = P.c; R.tA = P.t;
+  R.nA = min(kFramesPerRound, T - P.t);
+  R.nB = (straddle && P.c + 1 < B) ? kFramesPerRound - R.nA : 0;
+  return R;
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 3)
-logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
+logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, long long num_rounds, int straddle, int rpc,
               const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
               uint32_t* __restrict__ min_pow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -105,8 +147,9 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
   const int tid = threadIdx.x;
   const int g = tid >> 4;      // frame slot in the round
   const int j = tid & 15;      // lane within the frame group
-  const long long b = blockIdx.y;
-  const int t_chunk0 = blockIdx.x * kChunk;
+  const int rounds_per_clip = (T + kFramesPerRound - 1) / kFramesPerRound;
+  const long long r_begin = (long long)blockIdx.x * rpc;
+  const long long r_end = r_begin + rpc < num_rounds ? r_begin + rpc : num_rounds;
 
   constexpr bool kPcm = sizeof(TIn) == 2;
   constexpr int kVec = 16 / (int)sizeof(TIn);          // samples per 16-byte cp.async
@@ -116,25 +159,29 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
   const int nw = blob->n_weights;
   for (int i = tid; i < nw; i += kThreads) s_melw[i] = blob->mel_w[i];
 
-  const TIn* clip = wav + b * ld;
-  float* out_clip = db + b * 64 * (long long)T;
   float tmax = 0.f, tmin = INFINITY;
   // thread-constant twiddles kept in registers: W256^(j*2^i) (the other powers are products of these) and W512^j
   const float2 w1 = blob->tw256[1 * 16 + j], w2 = blob->tw256[2 * 16 + j], w4 = blob->tw256[4 * 16 + j], w8 = blob->tw256[8 * 16 + j];
   const float2 wj512 = blob->tw512[j];
-
-  // Stage the 2912 samples of a round into S.x[buf]: 16-byte cp.async for groups that lie inside the clip (and are
-  // 16-B aligned), synchronous loads with the reflect index map (no edge repeat) for the few groups at the clip edges.
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(clip) & 15) == 0);
   const int Li = (int)L;
-  auto stage = [&](int round, int buf) {
-    const int t0 = t_chunk0 + round * kFramesPerRound;
-    if (round < kRounds && t0 < T) {
-      const int s0 = t0 * UITK_HOP - UITK_N_FFT / 2;
+
+  // Stage the samples of round r into S.x[buf]: 16-byte cp.async for groups that lie inside their clip (and are 16-B
+  // aligned), synchronous loads with the reflect index map (no edge repeat) for the few groups at the clip edges.
+  auto stage = [&](long long r, RoundPos P, int buf) {
+    if (r < r_end) {
+      const Round R = round_at(P, T, B, straddle);
+      const int lenA = UITK_HOP * (R.nA - 1) + UITK_N_FFT;                       // floats of clip cA's range
+      const int total = R.nB > 0 ? lenA + UITK_HOP * (R.nB - 1) + UITK_N_FFT : lenA;
+      const TIn* clipA = wav + R.cA * ld;
+      const TIn* clipB = clipA + ld;
+      const bool okA = (reinterpret_cast<uintptr_t>(clipA) & 15) == 0, okB = (reinterpret_cast<uintptr_t>(clipB) & 15) == 0;
+      const int s0A = R.tA * UITK_HOP - UITK_N_FFT / 2;
       TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
-      for (int i = tid * kVec; i < kSamplesPerRound; i += kThreads * kVec) {
-        const int idx = s0 + i;
-        if (vec_ok && idx >= 0 && idx + kVec - 1 < Li) {
+      for (int i = tid * kVec; i < total; i += kThreads * kVec) {
+        const bool inA = i < lenA;                           // lenA is a multiple of kVec: a group never spans both clips
+        const TIn* clip = inA ? clipA : clipB;
+        const int idx = inA ? s0A + i : i - lenA - UITK_N_FFT / 2;
+        if ((inA ? okA : okB) && idx >= 0 && idx + kVec - 1 < Li) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(clip + idx)
                        : "memory");
         } else {
@@ -143,26 +190,32 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
             int id = idx + e;
             if (id < 0) id = -id;
             if (id >= Li) id = 2 * (Li - 1) - id;
-            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : TIn(0);      // frames past T read zeros
+            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : TIn(0);
           }
         }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stage(0, 0);
+  RoundPos pos = round_pos(r_begin, T, straddle, rounds_per_clip);
+  stage(r_begin, pos, 0);
 
-  for (int round = 0; round < kRounds; ++round) {
-    const int t0 = t_chunk0 + round * kFramesPerRound;
-    if (t0 >= T) break;
-    stage(round + 1, (round + 1) & 1);                 // buffer last read two barriers ago
+  int buf = 0;
+  for (long long r = r_begin; r < r_end; ++r, buf ^= 1) {
+    const RoundPos pos_next = next_pos(pos, T, straddle);
+    stage(r + 1, pos_next, buf ^ 1);                   // buffer last read two barriers ago
     asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();   // S.x[round & 1] (and the constants) visible; previous round's S.out readers are done
-    const TIn* sx = reinterpret_cast<const TIn*>(S.x[round & 1]);
+    __syncthreads();   // S.x[buf] (and the constants) visible; previous round's S.out readers are done
+    const TIn* sx = reinterpret_cast<const TIn*>(S.x[buf]);
+    const Round R = round_at(pos, T, B, straddle);
+    pos = pos_next;
+    const bool live = g < R.nA + R.nB;
+    const bool warp_live = (g & ~1) < R.nA + R.nB;     // warp-uniform: the warp's first frame group is live
 
+    if (warp_live) {
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
     float2 v[16];
-    const TIn* xf = sx + g * UITK_HOP;
+    const TIn* xf = sx + g * UITK_HOP + (g >= R.nA ? kStraddleShift : 0);
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const int n = j + 16 * m;
@@ -225,7 +278,6 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
     __syncwarp();
 
     // ---- sparse mel + dB
-    const bool live = (t0 + g) < T;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int m = j + 16 * q;
@@ -243,11 +295,17 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
       if (live) { tmax = fmaxf(tmax, acc); tmin = fminf(tmin, acc); }
       S.out[m * 17 + g] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));   // 10 log10(x); |err| ~1e-6 dB
     }
+    }   // warp_live
     __syncthreads();
-    for (int i = tid; i < 64 * kFramesPerRound; i += kThreads) {
-      const int m = i >> 4, gg = i & 15;
-      const int t = t0 + gg;
-      if (t < T) out_clip[(long long)m * T + t] = S.out[m * 17 + gg];
+    {   // S.out [64 mel][16 slots] -> db: this thread stores slot gg = tid & 15 of mel rows (tid >> 4) + 16 it
+      const int gg = tid & 15;
+      if (gg < R.nA + R.nB) {
+        const bool inA = gg < R.nA;
+        float* o = db + ((inA ? R.cA : R.cA + 1) * 64 + (tid >> 4)) * (long long)T + (inA ? R.tA + gg : gg - R.nA);
+        const float* so = S.out + (tid >> 4) * 17 + gg;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) o[(long long)it * 16 * T] = so[it * 16 * 17];
+      }
     }
   }
 
@@ -260,7 +318,7 @@ logmel_kernel(const TIn* __restrict__ wav, long long L, long long ld, int T,
   __syncthreads();
   if ((tid & 31) == 0) { S.red[tid >> 5] = tmax; S.red[8 + (tid >> 5)] = tmin; }
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && r_end > r_begin) {
     float m = S.red[0], mn = S.red[8];
 #pragma unroll
     for (int w = 1; w < kThreads / 32; ++w) { m = fmaxf(m, S.red[w]); mn = fminf(mn, S.red[8 + w]); }
@@ -282,15 +340,21 @@ static int launch_logmel_t(const TIn* wav, int64_t B, int64_t L, int64_t ld, con
                            uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
   const int64_t T = 1 + L / UITK_HOP;
   const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
+  static_assert(3 * (sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights + 1024) <= 228 * 1024, "three CTAs per SM");
   UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int chunks = (int)((T + kChunk - 1) / kChunk);
-  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
-    const int nb = (int)((B - b0) < 65535 ? (B - b0) : 65535);
-    dim3 grid(chunks, nb);
-    logmel_kernel<TIn><<<grid, kThreads, smem, s>>>(wav + b0 * ld, (long long)L, (long long)ld, (int)T, blob,
-                                                    db + b0 * 64 * T, max_pow, min_pow);
-    count_launches(1);
-  }
+  // rounds of 16 consecutive frames of the flat frame list (T >= 16), else per-clip rounds
+  const int straddle = T >= kFramesPerRound ? 1 : 0;
+  const int64_t num_rounds = straddle ? (B * T + kFramesPerRound - 1) / kFramesPerRound : B * ((T + kFramesPerRound - 1) / kFramesPerRound);
+  // 7 consecutive rounds per CTA.  Measured (scripts/logmel_time.py): persistent CTAs (one range per resident CTA) are
+  // 5 % SLOWER - the three CTAs of an SM then run their FFT (FMA-bound) and mel (LSU-bound) phases in lock step, while
+  // ordinary launch order staggers them; 4 / 14 / 28 rounds per CTA are 1-4 % slower than 7.
+  const int rpc = 7;
+  const int64_t grid64 = (num_rounds + rpc - 1) / rpc;
+  UITK_REQUIRE(grid64 < (1ll << 31), UITK_EINVAL, "too many frames for one launch");
+  const int grid = (int)grid64;
+  logmel_kernel<TIn><<<grid, kThreads, smem, s>>>(wav, (long long)B, (long long)L, (long long)ld, (int)T, (long long)num_rounds, straddle, rpc,
+                                                  blob, db, max_pow, min_pow);
+  count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;
 }

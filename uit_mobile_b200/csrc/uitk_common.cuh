@@ -32,7 +32,7 @@ void count_launches(int n);   // process-wide counter behind uitk_kernel_launche
 // ---------------------------------------------------------------------------------------------------------
 // Front-end constant blob (device layout).  All fields 4 bytes; header first.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kMaxMelWeights = 2048;   // packed filterbank entries kept in shared memory (HTK/64: 1024 incl. padding)
+constexpr int kMaxMelWeights = 1792;   // packed filterbank entries kept in shared memory (HTK/64: 1024 incl. padding)
 
 struct FrontendBlob {
   int magic;                 // 'UFE1'
