@@ -85,6 +85,21 @@ def test_logmel_vs_reference_golden(name):
         assert np.abs(got - ref).max() <= 2e-4          # typical: a few 1e-5 dB
 
 
+@pytest.mark.parametrize("B,L", [(5, 1000), (3, 2400), (7, 2560), (5, 16000), (2, 16384), (9, 4810), (1, 300)])
+def test_logmel_flat_frame_rounds_vs_oracle(B, L):
+    """The kernel cuts the batch's B*T frames into rounds of 16 that may straddle clips (T >= 16) or not (T < 16):
+    odd batch sizes / frame counts (T = 7, 16, 17, 101, 103, 31, 2) against the torch-CPU oracle of the reference front-end."""
+    from oracle import uit_oracle as O
+    m = model("uit_xxxs")
+    sd = H.make_state_dict("uit_xxxs")
+    x = H.noise_clips(B, L, seed=100 + L)
+    x[-1, : L // 2] *= 1e-3                                    # a quiet stretch: dynamic range across clips
+    ref = O.logmel(torch.from_numpy(x), sd["front_end.0.spectrogram.window"], sd["front_end.0.mel_scale.fb"]).numpy()
+    got = m.front_end(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert got.shape == ref.shape == (B, 64, 1 + L // 160)
+    assert_logmel_close(got, x, ref)
+
+
 def test_logmel_q2_batch_global_cutoff():
     m = model("uit_xxxs")
     got = m.front_end(torch.from_numpy(INPUTS["adversarial"]).to(DEV)).cpu().numpy()

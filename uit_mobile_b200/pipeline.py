@@ -2,7 +2,8 @@
 
 This is what a caller sitting where the reference's DataLoader/`inference.py` sits uses when the audio is in host
 memory (reference: evaluate.py:53-66 moves every batch host->device and reads the scores back).  The batch is cut
-into chunks; the H2D copy of chunk i+1 (second stream) overlaps the log-mel AND encoder kernels of chunk i.
+into chunks; the H2D copy of chunk i+1 (second stream) overlaps the log-mel AND encoder kernels of chunk i, and the
+scores of every chunk travel back on a third stream under the following uploads.
 
 The reference's top-dB cutoff is batch-global (Q2: max over the whole batch - 120 dB), which would force the encoder
 to wait for the last chunk's front-end.  Instead every chunk is encoded *speculatively* with the running maximum of
@@ -55,6 +56,7 @@ class HostPipeline:
         self.words_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.words_init = torch.tensor([0, _INF_BITS], dtype=torch.int32, device=dev)
         self.copy_stream = torch.cuda.Stream(dev)
+        self.d2h_stream = torch.cuda.Stream(dev)       # PCIe is full duplex: scores of chunk i go back under the H2D of chunk i+2
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.respeculated = 0          # how many calls needed the exact re-run
@@ -94,14 +96,21 @@ class HostPipeline:
             free[i & 1] = done
             if spec:
                 m.encode(db_i, max_w, out=self.probs[b0:b0 + nb])
+                scored = torch.cuda.Event()
+                scored.record(main)
+                with torch.cuda.stream(self.d2h_stream):
+                    self.d2h_stream.wait_event(scored)
+                    self.out_host[b0:b0 + nb].copy_(self.probs[b0:b0 + nb], non_blocking=True)
         if sharded:
             torch.distributed.all_reduce(max_w, op=torch.distributed.ReduceOp.MAX, group=m.process_group)
         if not spec:
             m.encode(self.db[:B], max_w, out=self.probs[:B])
         out = self.out_host[:B]
-        out.copy_(self.probs[:B], non_blocking=True)
+        if not spec:
+            out.copy_(self.probs[:B], non_blocking=True)
         self.words_host.copy_(self.words, non_blocking=True)
         main.synchronize()
+        self.d2h_stream.synchronize()
         if spec:
             mx, mn = int(self.words_host[0]), int(self.words_host[1])
             if _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:      # conservative margin vs the device's log2-based dB
