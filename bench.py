@@ -342,6 +342,33 @@ def run_b200(args):
                                 "clips_per_s": n10 / (ms10 * 1e-3), "achieved": gbs10, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                                 "frac": gbs10 / peaks["hbm_gbs"], "bytes_per_clip": bytes10, "ms_per_launch": ms10}
         del x10
+        # BASELINE config 5 shape, one GPU's share (57.6 M samples / 8 GPUs): sliding 1 s windows, hop 1600, over one stream
+        n_s, hop_s = 7_200_000, 1600
+        stream = (0.1 * torch.randn(n_s, generator=g, device=dev)).clamp_(-1, 1)
+        n_win = (n_s - 16000) // hop_s + 1
+
+        def per_window():       # every window runs the whole front-end (windows read in place, row stride = hop)
+            db_w, mp_w = model.front_end.logmel_unclamped(stream, ld=hop_s, B=n_win, L=16000)
+            return model.encode(db_w, mp_w)
+
+        ms_sl = {}
+        for name, fn in (("per_window_frontend", per_window), ("shared_stft", lambda: model.forward_sliding(stream, hop=hop_s))):
+            for _ in range(2):
+                y_sl = fn()
+            torch.cuda.synchronize()
+            f0, f1 = ev(), ev()
+            f0.record()
+            for _ in range(5):
+                y_sl = fn()
+            f1.record()
+            torch.cuda.synchronize()
+            ms_sl[name] = (f0.elapsed_time(f1) / 5, y_sl)
+        line["sliding_windows"] = {
+            "workload": f"{n_win} sliding 1 s windows, hop {hop_s}, over one {n_s}-sample stream (BASELINE config 5, one GPU's share)",
+            "windows_per_s": n_win / (ms_sl["shared_stft"][0] * 1e-3), "ms": ms_sl["shared_stft"][0],
+            "ms_per_window_frontend": ms_sl["per_window_frontend"][0],
+            "bit_identical_to_per_window_path": bool(torch.equal(ms_sl["shared_stft"][1], ms_sl["per_window_frontend"][1]))}
+        del stream
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         xs = x_host[:CPU_SAMPLE_CLIPS].clone()

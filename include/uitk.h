@@ -96,6 +96,18 @@ UITK_API int uitk_logmel(const float* d_wav, int64_t B, int64_t L, int64_t ld_wa
 UITK_API int uitk_logmel_i16(const int16_t* d_pcm, int64_t B, int64_t L, int64_t ld_pcm, const void* d_frontend_blob,
                     float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* stream);
 
+/* Sliding 1 s (or any) windows over ONE long stream, window hop a multiple of the STFT hop (the reference
+ * has no such entry point - its callers slice the waveform and run front_end per slice, uit.py:455 / 468-472).
+ * Produces exactly what uitk_logmel(d_stream, W, window, hop, ...) produces for the W = (n_samples - window)/hop + 1
+ * overlapping windows - bit-identical d_db [W, 64, 1 + window/160] and max/min words - but computes every interior STFT
+ * frame of the stream ONCE (a window frame t in [2, T-2) does not touch the window's reflect padding, so it is frame
+ * w*hop/160 + t of the stream) and only the 4 edge frames per window separately.
+ *   d_workspace  uitk_logmel_sliding_workspace_bytes(n_samples) bytes: the stream's log-mel [64, 1 + n_samples/160] */
+UITK_API size_t uitk_logmel_sliding_workspace_bytes(int64_t n_samples);
+UITK_API int uitk_logmel_sliding(const float* d_stream, int64_t n_samples, int64_t window, int64_t hop, const void* d_frontend_blob,
+                        float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120). */
 UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream);
 

@@ -121,6 +121,30 @@ def test_logmel_sliding_windows_strided_view():
     assert torch.equal(db_v, db_c) and torch.equal(mp_v, mp_c)
 
 
+@pytest.mark.parametrize("hop,n", [(1600, 16000 * 6), (160, 16000 + 160 * 37), (16000, 16000 * 3), (4800, 16000 * 4 + 777), (1600, 16000)])
+def test_logmel_sliding_stft_reuse_is_bit_identical(hop, n):
+    """interior STFT frames shared between overlapping windows; edge frames (reflect padding) per window.
+    Must equal the per-window front-end bit for bit, including the batch max / min words."""
+    m = model("uit_xxxs")
+    stream = torch.from_numpy(H.noise_clips(1, n, seed=5 + hop)[0]).to(DEV)
+    stream[n // 3: n // 3 + 4000] *= 1e-3
+    W = (n - 16000) // hop + 1
+    mn_a = torch.full((1,), 0x7F800000, dtype=torch.int32, device=DEV)
+    mn_b = mn_a.clone()
+    db_a, mp_a = m.front_end.logmel_unclamped(stream, ld=hop, B=W, L=16000, min_pow=mn_a)
+    db_b, mp_b = m.front_end.logmel_sliding(stream, 16000, hop, min_pow=mn_b)
+    assert db_a.shape == db_b.shape == (W, 64, 101)
+    assert torch.equal(db_a, db_b) and torch.equal(mp_a, mp_b) and torch.equal(mn_a, mn_b)
+
+
+def test_forward_sliding_equals_forward_on_unfolded_windows():
+    m = model("uit_xxxs", precision="bf16")
+    stream = torch.from_numpy(H.noise_clips(1, 16000 * 5, seed=77)[0]).to(DEV)
+    ref = m(stream.unfold(0, 16000, 1600).contiguous())
+    got = m.forward_sliding(stream, hop=1600)
+    assert torch.equal(ref, got)
+
+
 @pytest.mark.parametrize("depth", [1, 2, 4])
 def test_fp32_encoder_block_trace(depth):
     """Token activations after block `depth` vs the reference trace (a depth-truncated model is packed)."""

@@ -57,6 +57,43 @@ int uitk_logmel_i16(const int16_t* d_pcm, int64_t B, int64_t L, int64_t ld_pcm, 
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t uitk_logmel_sliding_workspace_bytes(int64_t n_samples) {
+  return n_samples < 0 ? 0 : (size_t)64 * (size_t)(1 + n_samples / UITK_HOP) * sizeof(float);
+}
+
+int uitk_logmel_sliding(const float* d_stream, int64_t n_samples, int64_t window, int64_t hop, const void* d_frontend_blob, float* d_db,
+                        uint32_t* d_max_pow, uint32_t* d_min_pow, void* d_workspace, size_t workspace_bytes, void* stream) {
+  UITK_REQUIRE(d_stream && d_frontend_blob && d_db && d_max_pow && d_workspace, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(hop >= UITK_HOP && hop % UITK_HOP == 0, UITK_EINVAL,
+               "window hop %lld must be a positive multiple of the STFT hop (160); use uitk_logmel with ld_wav = hop otherwise", (long long)hop);
+  UITK_REQUIRE(window >= 4 * UITK_HOP && window % UITK_HOP == 0 && window <= (1ll << 30), UITK_EINVAL,
+               "window %lld must be a multiple of 160 samples, at least 640", (long long)window);
+  UITK_REQUIRE(n_samples >= window && n_samples <= (1ll << 30), UITK_EINVAL, "stream shorter than one window (or longer than 2^30 samples)");
+  UITK_REQUIRE(aligned(d_stream, 4) && aligned(d_db, 4) && aligned(d_max_pow, 4) && aligned(d_frontend_blob, 16) && aligned(d_workspace, 4),
+               UITK_EALIGN, "misaligned pointer");
+  UITK_REQUIRE(workspace_bytes >= uitk_logmel_sliding_workspace_bytes(n_samples), UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
+               uitk_logmel_sliding_workspace_bytes(n_samples), workspace_bytes);
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  const FrontendBlob* blob = reinterpret_cast<const FrontendBlob*>(d_frontend_blob);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t W = (n_samples - window) / hop + 1;          // windows
+  const int64_t Tw = 1 + window / UITK_HOP;                  // frames per window
+  const int64_t r = hop / UITK_HOP;                          // window hop in frames
+  const int64_t U = 1 + n_samples / UITK_HOP;                // frames of the stream taken as one clip
+  float* G = reinterpret_cast<float*>(d_workspace);          // [64][U]
+  // A window frame t in [2, Tw-2) lies wholly inside the window: it IS frame w*r + t of the stream.  Compute the stream's
+  // frames 2 .. (W-1)*r + Tw - 3 once (every one of them is an interior frame of some window, so they all count for the
+  // batch max / min), scatter them into the windows, and compute only the 4 reflect-padded edge frames per window.
+  rc = launch_logmel_frames(d_stream, 1, n_samples, n_samples, blob, G, 2, (W - 1) * r + Tw - 4, 64 * U, U, d_max_pow, d_min_pow, s);
+  if (rc != UITK_OK) return rc;
+  rc = launch_window_gather(G, U, d_db, W, (int)Tw, (int)r, s);
+  if (rc != UITK_OK) return rc;
+  rc = launch_logmel_frames(d_stream, W, window, hop, blob, d_db, 0, 2, 64 * Tw, Tw, d_max_pow, d_min_pow, s);
+  if (rc != UITK_OK) return rc;
+  return launch_logmel_frames(d_stream, W, window, hop, blob, d_db, Tw - 2, 2, 64 * Tw, Tw, d_max_pow, d_min_pow, s);
+}
+
 int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream) {
   UITK_REQUIRE(d_db && d_max_pow, UITK_EINVAL, "null pointer");
   UITK_REQUIRE(n >= 0, UITK_EINVAL, "negative size");

@@ -137,9 +137,12 @@ __device__ __forceinline__ Round round_at(RoundPos P, int T, long long B, int st
 
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 3)
-logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, long long num_rounds, int straddle, int rpc,
+logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, int t0, long long out_bs, long long out_ms,
+              long long num_rounds, int straddle, int rpc,
               const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
               uint32_t* __restrict__ min_pow) {
+  // T = frames computed per clip: frames t0 .. t0 + T - 1 of the clip's 1 + L/160.  Output element (clip, mel, frame t) goes
+  // to db[clip * out_bs + mel * out_ms + t].
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   float* s_melw = reinterpret_cast<float*>(smem_raw + sizeof(SmemLayout));
@@ -175,12 +178,13 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
       const TIn* clipA = wav + R.cA * ld;
       const TIn* clipB = clipA + ld;
       const bool okA = (reinterpret_cast<uintptr_t>(clipA) & 15) == 0, okB = (reinterpret_cast<uintptr_t>(clipB) & 15) == 0;
-      const int s0A = R.tA * UITK_HOP - UITK_N_FFT / 2;
+      const int s0A = (t0 + R.tA) * UITK_HOP - UITK_N_FFT / 2;
+      const int s0B = t0 * UITK_HOP - UITK_N_FFT / 2;
       TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
       for (int i = tid * kVec; i < total; i += kThreads * kVec) {
         const bool inA = i < lenA;                           // lenA is a multiple of kVec: a group never spans both clips
         const TIn* clip = inA ? clipA : clipB;
-        const int idx = inA ? s0A + i : i - lenA - UITK_N_FFT / 2;
+        const int idx = inA ? s0A + i : s0B + (i - lenA);
         if ((inA ? okA : okB) && idx >= 0 && idx + kVec - 1 < Li) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(clip + idx)
                        : "memory");
@@ -301,10 +305,10 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
       const int gg = tid & 15;
       if (gg < R.nA + R.nB) {
         const bool inA = gg < R.nA;
-        float* o = db + ((inA ? R.cA : R.cA + 1) * 64 + (tid >> 4)) * (long long)T + (inA ? R.tA + gg : gg - R.nA);
+        float* o = db + (inA ? R.cA : R.cA + 1) * out_bs + (tid >> 4) * out_ms + t0 + (inA ? R.tA + gg : gg - R.nA);
         const float* so = S.out + (tid >> 4) * 17 + gg;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) o[(long long)it * 16 * T] = so[it * 16 * 17];
+        for (int it = 0; it < 4; ++it) o[it * 16 * out_ms] = so[it * 16 * 17];
       }
     }
   }
@@ -337,8 +341,13 @@ __global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint3
 
 template <typename TIn>
 static int launch_logmel_t(const TIn* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db,
-                           uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
-  const int64_t T = 1 + L / UITK_HOP;
+                           uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s, int64_t t0 = 0, int64_t tn = -1, int64_t out_bs = -1,
+                           int64_t out_ms = -1) {
+  const int64_t Tall = 1 + L / UITK_HOP;
+  const int64_t T = tn < 0 ? Tall : tn;                                      // frames computed per clip
+  if (out_ms < 0) out_ms = Tall;
+  if (out_bs < 0) out_bs = 64 * Tall;
+  if (T == 0 || B == 0) return UITK_OK;
   const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
   static_assert(3 * (sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights + 1024) <= 228 * 1024, "three CTAs per SM");
   UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -352,8 +361,42 @@ static int launch_logmel_t(const TIn* wav, int64_t B, int64_t L, int64_t ld, con
   const int64_t grid64 = (num_rounds + rpc - 1) / rpc;
   UITK_REQUIRE(grid64 < (1ll << 31), UITK_EINVAL, "too many frames for one launch");
   const int grid = (int)grid64;
-  logmel_kernel<TIn><<<grid, kThreads, smem, s>>>(wav, (long long)B, (long long)L, (long long)ld, (int)T, (long long)num_rounds, straddle, rpc,
-                                                  blob, db, max_pow, min_pow);
+  logmel_kernel<TIn><<<grid, kThreads, smem, s>>>(wav, (long long)B, (long long)L, (long long)ld, (int)T, (int)t0, (long long)out_bs,
+                                                  (long long)out_ms, (long long)num_rounds, straddle, rpc, blob, db, max_pow, min_pow);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+namespace {
+
+// db_w[w][m][t] = G[m][w * r + t] for the interior frames t in [2, Tw - 2) of every window (sliding-window reuse, see api.cu)
+__global__ void window_gather_kernel(const float* __restrict__ G, long long U, float* __restrict__ dbw, long long W, int Tw, int r) {
+  const int inner = Tw - 4;
+  const long long total = W * 64 * inner;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int t = (int)(i % inner) + 2;
+    const long long wm = i / inner;
+    const int m = (int)(wm & 63);
+    const long long w = wm >> 6;
+    dbw[(w * 64 + m) * Tw + t] = __ldg(G + (long long)m * U + w * r + t);
+  }
+}
+
+}  // namespace
+
+int launch_logmel_frames(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db, int64_t t0, int64_t tn,
+                         int64_t out_bs, int64_t out_ms, uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s) {
+  return launch_logmel_t<float>(wav, B, L, ld, blob, db, max_pow, min_pow, s, t0, tn, out_bs, out_ms);
+}
+
+int launch_window_gather(const float* G, int64_t U, float* dbw, int64_t W, int Tw, int r, cudaStream_t s) {
+  if (W == 0 || Tw <= 4) return UITK_OK;
+  const long long total = W * 64 * (long long)(Tw - 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  window_gather_kernel<<<(int)blocks, 256, 0, s>>>(G, (long long)U, dbw, (long long)W, Tw, r);
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;

@@ -213,6 +213,35 @@ class FrontEnd(nn.Sequential):
         return out, max_pow
 
 
+def _logmel_sliding(front_end, stream: torch.Tensor, window: int = 16000, hop: int = 1600,
+                    max_pow: Optional[torch.Tensor] = None, min_pow: Optional[torch.Tensor] = None):
+    """Log-mel of all sliding windows of ONE long stream.  Same result, bit for bit, as
+    ``logmel_unclamped(stream, ld=hop, B=W, L=window)``; when ``hop`` is a multiple of 160 the interior STFT frames are
+    computed once for the stream instead of once per overlapping window (10x less front-end work at hop 1600)."""
+    if not stream.is_cuda or stream.dtype != torch.float32 or stream.dim() != 1 or not stream.is_contiguous():
+        raise N.UitkError("expected a contiguous 1-D float32 CUDA tensor (the stream)")
+    n = stream.numel()
+    if n < window:
+        raise ValueError("stream shorter than one window")
+    W = (n - window) // hop + 1
+    if hop % 160 != 0 or window % 160 != 0:
+        return front_end.logmel_unclamped(stream, ld=hop, B=W, L=window, max_pow=max_pow, min_pow=min_pow)
+    l = N.lib()
+    T = int(l.uitk_num_frames(window))
+    out = torch.empty((W, 64, T), dtype=torch.float32, device=stream.device)
+    if max_pow is None:
+        max_pow = torch.zeros(1, dtype=torch.int32, device=stream.device)
+    ws = torch.empty(int(l.uitk_logmel_sliding_workspace_bytes(n)), dtype=torch.uint8, device=stream.device)
+    with torch.cuda.device(stream.device):
+        N.check(l.uitk_logmel_sliding(stream.data_ptr(), n, window, hop, front_end._blob(stream.device).data_ptr(), out.data_ptr(),
+                                      max_pow.data_ptr(), None if min_pow is None else min_pow.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream(stream.device).cuda_stream), "uitk_logmel_sliding")
+    return out, max_pow
+
+
+FrontEnd.logmel_sliding = _logmel_sliding
+
+
 class UITBase(nn.Module):
     """uit.py:252-493, inference path only (eval mode, pooling='mean', BNeckAttention, ReLU MLP, init_bn)."""
 
@@ -398,6 +427,20 @@ class UITBase(nn.Module):
             # Q2: the top-dB cutoff is batch-global; with the batch sharded over GPUs the scope is the global batch.
             torch.distributed.all_reduce(max_pow, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
         return self.encode(db, max_pow)
+
+
+def _forward_sliding(self, stream: torch.Tensor, hop: int = 1600, window: int = 16000) -> torch.Tensor:
+    """Scores of all sliding windows of one long stream: exactly ``self(stream.unfold(0, window, hop))`` (one top-dB scope over all
+    windows, Q2), with the stream's STFT shared between overlapping windows (``FrontEnd.logmel_sliding``)."""
+    if self.training:
+        raise NotImplementedError("uit_mobile_b200 implements inference only: call model.eval()")
+    db, max_pow = self.front_end.logmel_sliding(stream, window, hop)
+    if self.process_group is not None:
+        torch.distributed.all_reduce(max_pow, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
+    return self.encode(db, max_pow)
+
+
+UITBase.forward_sliding = _forward_sliding
 
 
 def _factory(depth: int, kwargs) -> UITBase:
