@@ -91,7 +91,7 @@ static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct TcParams {
   const unsigned char* wts;     // bf16 section
-  const float* patch_b; const float* time_pos; const float* freq_pos;
+  const float* pos_tab;         // [24][128] conv bias + time_pos + freq_pos per token of a crop
   const float* bn_scale; const float* bn_shift;
   const float* norm_w; const float* norm_b;
   const float* db; const uint32_t* max_pow;
@@ -519,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
       TR(0, 3);
-      {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383), written back to TMEM once
-        const int tok = r % tokens, f = tok / t_n, tau = tok - f * t_n;
+      {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383; one pre-added table row per token), back to TMEM
+        const float* pt = p.pos_tab + (r % tokens) * 128;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float v[32];
@@ -530,11 +530,8 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           if (r < rows_valid) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 pb = __ldg(reinterpret_cast<const float4*>(p.patch_b + c0 + i));
-              const float4 tp = __ldg(reinterpret_cast<const float4*>(p.time_pos + tau * 128 + c0 + i));
-              const float4 fp = __ldg(reinterpret_cast<const float4*>(p.freq_pos + f * 128 + c0 + i));
-              v[i] = (v[i] + pb.x) + tp.x + fp.x; v[i + 1] = (v[i + 1] + pb.y) + tp.y + fp.y;
-              v[i + 2] = (v[i + 2] + pb.z) + tp.z + fp.z; v[i + 3] = (v[i + 3] + pb.w) + tp.w + fp.w;
+              const float4 pb = __ldg(reinterpret_cast<const float4*>(pt + c0 + i));
+              v[i] += pb.x; v[i + 1] += pb.y; v[i + 2] += pb.z; v[i + 3] += pb.w;
             }
           }
           tmem_st32(tx + c0, v);
@@ -810,7 +807,7 @@ int run_encoder_tc(const EncoderArgs& a) {
 
   TcParams p{};
   p.wts = blob + bf16_off;
-  p.patch_b = W + lay.patch_b; p.time_pos = W + lay.time_pos; p.freq_pos = W + lay.freq_pos;
+  p.pos_tab = W + lay.pos_tab;
   p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift;
   p.norm_w = W + lay.norm_w; p.norm_b = W + lay.norm_b;
   p.db = a.db; p.max_pow = a.max_pow;

@@ -41,6 +41,7 @@ EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
   l.norm_w = take(cur, 128); l.norm_b = take(cur, 128);
   l.hln_w = take(cur, 128); l.hln_b = take(cur, 128);
   l.cb_final = take(cur, 128);
+  l.pos_tab = take(cur, 24 * 128);
   l.head_wt = take(cur, (size_t)128 * l.outputdim_padded); l.head_b = take(cur, l.outputdim_padded);
   l.blocks = cur;
   size_t b = 0;
@@ -302,6 +303,10 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
   }
   memcpy(W + l.cb_final, cb.data(), 128 * 4);
+  if (cfg->grid_t >= 6)
+    for (int tok = 0; tok < 24; ++tok)
+      for (int c = 0; c < 128; ++c)
+        W[l.pos_tab + (size_t)tok * 128 + c] = (t[5][c] + t[6][(size_t)c * cfg->grid_t + tok % 6]) + t[7][(size_t)c * 4 + tok / 6];
   return UITK_OK;
 }
 

@@ -65,7 +65,8 @@ struct EncoderLayout {
   size_t patch_wt, patch_b;           // [256][128], [128]
   size_t time_pos, freq_pos;          // [grid_t][128], [4][128]
   size_t norm_w, norm_b, hln_w, hln_b;
-  size_t cb_final;                    // [128] sum of all deferred proj/fc2 biases (tensor-core path)
+  size_t cb_final;                    // [128] sum of all proj/fc2 biases (kept for blob compatibility; unused)
+  size_t pos_tab;                     // [24][128] conv bias + time_pos[tok % 6] + freq_pos[tok / 6] (tensor-core path, 24-token crops)
   size_t head_wt, head_b;             // [128][outputdim_padded], [outputdim_padded]
   int outputdim_padded;
   size_t blocks;                      // first block
