@@ -455,16 +455,89 @@ __global__ void __launch_bounds__(256) head_pooled_kernel(const float* __restric
 }
 }  // namespace
 
+// Single-crop head: probs[B][outputdim] = sigmoid(LayerNorm_1e-5(pooled[B][128]) W^T + b) as one fp32 GEMM.
+// 64 clips x 64 classes per CTA, the whole K = 128 resident in shared memory (one load phase, no k-loop barriers),
+// 4 x 4 outputs per thread.  576 CTAs for 4096 clips: the first version (128 x 128 tiles, 160 CTAs) left most SMs with one
+// 8-warp CTA and took 54 us of the encoder's 460; this one is latency-hidden by 3-4 resident CTAs per SM.
+namespace {
+constexpr int kHM = 64, kHN = 64, kHLd = 132;
+__global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ pooled, int B, const float* __restrict__ hln_w,
+                                                        const float* __restrict__ hln_b, const float* __restrict__ head_wt,
+                                                        const float* __restrict__ head_b, int outputdim, int ld_head,
+                                                        float* __restrict__ probs) {
+  extern __shared__ __align__(16) float hs[];
+  float* As = hs;                      // [64][132] normalised features
+  float* Ws = hs + kHM * kHLd;         // [128][64] weight tile (k-major rows)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * kHM, n0 = blockIdx.y * kHN;
+  for (int idx = tid; idx < 128 * (kHN / 4); idx += 256) {
+    const int k = idx >> 4, c4 = idx & 15;
+    *reinterpret_cast<float4*>(&Ws[k * kHN + c4 * 4]) = __ldg(reinterpret_cast<const float4*>(head_wt + (size_t)k * ld_head + n0 + c4 * 4));
+  }
+  const float4 hg = __ldg(reinterpret_cast<const float4*>(hln_w + lane * 4));
+  const float4 hb = __ldg(reinterpret_cast<const float4*>(hln_b + lane * 4));
+#pragma unroll
+  for (int i = 0; i < kHM / 8; ++i) {               // warp w normalises rows w*8 .. w*8+7 (one float4 per lane)
+    const int r = warp * (kHM / 8) + i, row = row0 + r;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < B) m = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)row * 128 + lane * 4));
+    float sum = m.x + m.y + m.z + m.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / 128.f);
+    const float d0 = m.x - mean, d1 = m.y - mean, d2 = m.z - mean, d3 = m.w - mean;
+    float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
+    *reinterpret_cast<float4*>(&As[r * kHLd + lane * 4]) =
+        make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 128; k += 4) {
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty * 4 + i) * kHLd + k]);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[(k + kk) * kHN + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+        acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+        acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+      }
+    }
+  }
+  const int col0 = n0 + tx * 4;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(head_b + col0));        // head_b is zero padded to ld_head
+  const float bj[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + ty * 4 + i;
+    if (row >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j < outputdim) probs[(size_t)row * outputdim + col0 + j] = 1.f / (1.f + expf(-(acc[i][j] + bj[j])));
+  }
+}
+}  // namespace
+
 int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim,
                        int eval_max, float* probs, cudaStream_t s) {
   if (crops == 1 && B < (1ll << 31) - 256) {
     // single crop: one tiled fp32 GEMM [B,128] x [128,outputdim] with the head LayerNorm as prologue and the sigmoid as
     // epilogue (every weight tile fetched from L2 feeds 128 clips)
-    GemmParams g{};
-    g.M = (int)B; g.K = 128; g.A = pooled; g.lda = 128; g.Wt = W + lay.head_wt; g.ldw = lay.outputdim_padded;
-    g.bias = W + lay.head_b; g.C = probs; g.ldc = outputdim; g.n_valid = outputdim;
-    g.ln_w = W + lay.hln_w; g.ln_b = W + lay.hln_b; g.ln_eps = 1e-5f;
-    gemm_kernel<128, PRO_LN, EPI_SIGMOID><<<dim3((unsigned)((B + BM - 1) / BM), lay.outputdim_padded / 128), 256, 0, s>>>(g);
+    const int smem = (kHM * kHLd + 128 * kHN) * (int)sizeof(float);        // 66.5 KB
+    UITK_CHECK_CUDA(cudaFuncSetAttribute(head_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    head_gemm_kernel<<<dim3((unsigned)((B + kHM - 1) / kHM), (unsigned)((outputdim + kHN - 1) / kHN)), 256, smem, s>>>(
+        pooled, (int)B, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, probs);
     count_launches(1);
     UITK_CHECK_CUDA(cudaGetLastError());
     return UITK_OK;
