@@ -248,7 +248,7 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     transpose_into(Wb + l.blk.fc1_wt, b[8], 384, 128, 384); memcpy(Wb + l.blk.fc1_b, b[9], 384 * 4);
     transpose_into(Wb + l.blk.fc2_wt, b[10], 128, 384, 128); memcpy(Wb + l.blk.fc2_b, b[11], 128 * 4);
   }
-  // deferred-bias vectors of the tensor-core path: cb1(i) = sum_{j<i} (proj_b_j + fc2_b_j), cb2(i) = cb1(i) + proj_b_i
+  // cb = running sum of all proj / fc2 biases (cb_final keeps the blob layout of earlier versions; no kernel reads it)
   std::vector<float> cb(128, 0.f);
   unsigned char* sec = reinterpret_cast<unsigned char*>(h_blob) + sizeof(BlobHeader) + fp32_section_bytes(l);
   if (cfg->precision == UITK_PREC_BF16) {
