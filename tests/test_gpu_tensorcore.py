@@ -144,3 +144,19 @@ def test_bf16_vs_fp32_device_paths_over_shapes(L):
         yb, yf = mb(x), mf(x)
         assert yb.shape == yf.shape == (B, 537) and torch.isfinite(yb).all()
         assert (yb - yf).abs().max().item() <= TOL["init"], (L, B)
+
+
+def test_bf16_full_size_config3_periodicity():
+    """BASELINE config 3 size on one GPU (UiT-XXS, 65 520 x 1 s clips in ONE forward): a batch made of 16 copies of a 4095-clip
+    base (a multiple of the 5-clip tile, so every copy sits at the same in-tile positions and the batch maximum is the same)
+    must give 16 bit-identical copies of the base scores - size-independent property at the full size, through every
+    launch-splitting path of encode()."""
+    m = _model("uit_xxs", "trained", "bf16")
+    g = torch.Generator(device=DEV).manual_seed(11)
+    base = (0.1 * torch.randn(4095, 16000, generator=g, device=DEV)).clamp_(-1, 1)
+    base[7] *= 1e-4                                             # a quiet clip: large dynamic range inside the batch
+    with torch.no_grad():
+        y_base = m(base)
+        y_big = m(base.repeat(16, 1))
+    assert y_big.shape == (65520, 537) and torch.isfinite(y_big).all()
+    assert torch.equal(y_big.view(16, 4095, 537), y_base.unsqueeze(0).expand(16, -1, -1))
