@@ -282,6 +282,20 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // The dB rows of a tile come from HBM (the log-mel of a 4096-clip batch does not survive in L2 next to the waveforms)
+        // and the patch gather is latency-bound on them: pull the NEXT tile's clips into L2 now, a whole tile ahead.
+        if (p.crops == 1 && tile + (int)gridDim.x < p.num_tiles && elect_one()) {
+          const int rr_next = (tile + (int)gridDim.x) * p.G;
+          const int n_next = min(p.G, p.RR - rr_next);
+          const size_t clip_bytes = (size_t)64 * p.T * sizeof(float);
+          const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.db) + (size_t)rr_next * clip_bytes;
+          const uintptr_t a1 = (a0 + (size_t)n_next * clip_bytes) & ~(uintptr_t)15;
+          for (uintptr_t a = (a0 + 15) & ~(uintptr_t)15; a < a1; a += 32768) {
+            const uintptr_t left = a1 - a;
+            bulk_prefetch_l2(reinterpret_cast<const void*>(a), (uint32_t)(left < 32768 ? left : 32768));
+          }
+        }
+        __syncwarp();
         const unsigned char* wb = p.wts;
         for (int c = 0; c < 4; ++c) ring_load(wb, kTile);
         for (int blk = 0; blk < p.depth; ++blk) {                 // same order as the MMA issuer consumes (pack.cu)
@@ -481,37 +495,35 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           const int rz = rows_valid + i / 16, k8 = i % 16;
           *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
         }
+        // tokens == 24 (t_n == 6: 96 frames = 3 x 32 lanes, no tail predicate).  Element (mel row u, frame tt = lane + 32 j):
+        // k = (dfl0 + u) * 16 + (lane & 15), row = g * 24 + f * 6 + 2 j + (lane >> 4)  ->  shared offset = per-lane base
+        // + u * 4096 + j * 32 + g * 384 with compile-time u, j terms: the stores need no address arithmetic.
         const int f = warp >> 1, dfl0 = 4 * (warp & 1);
+        const int mel0 = 16 * f + 8 * half + dfl0;
+        unsigned char* lane_dst = smem + OFF_A + (2 * dfl0 + ((lane & 15) >> 3)) * 2048 + (f * 6 + (lane >> 4)) * 16 + (lane & 7) * 2;
+        float sc[4], sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sc[u] = __ldg(p.bn_scale + mel0 + u); sh[u] = __ldg(p.bn_shift + mel0 + u); }
+#pragma unroll 1
         for (int g = 0; g < g_cnt; ++g) {
           const int rr = rr0 + g;
           const int b = rr / p.crops, c = rr - b * p.crops;
           int start = 0;
           if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
-          const int mel0 = 16 * f + 8 * half + dfl0;
-          const float* src0 = p.db + ((size_t)b * 64 + mel0) * p.T + start;
+          const float* src = p.db + ((size_t)b * 64 + mel0) * p.T + start + lane;
           float val[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) val[u][j] = __ldg(src + 32 * j);
+            src += p.T;
+          }
+          unsigned char* d = lane_dst + g * (24 * 16);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int tt = lane + 32 * j;
-              val[u][j] = tt < 16 * t_n ? __ldg(src0 + (size_t)u * p.T + tt) : 0.f;
-            }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float sc = __ldg(p.bn_scale + mel0 + u), sh = __ldg(p.bn_shift + mel0 + u);
-            const int rbase = g * tokens + f * t_n;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int tt = lane + 32 * j;
-              if (tt < 16 * t_n) {
-                const float y = fmaf(fmaxf(val[u][j], cutoff), sc, sh);
-                const int k = (dfl0 + u) * 16 + (tt & 15);                 // k within the half
-                const int rrow = rbase + (tt >> 4);
-                *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + (k >> 3) * 2048 + rrow * 16 + (k & 7) * 2) = __float2bfloat16_rn(y);
-              }
-            }
-          }
+            for (int j = 0; j < 3; ++j)
+              *reinterpret_cast<__nv_bfloat16*>(d + u * 4096 + j * 32) = __float2bfloat16_rn(fmaf(fmaxf(val[u][j], cutoff), sc[u], sh[u]));
         }
         signal_ready();
       }
