@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 102
+#define UITK_VERSION 103
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
