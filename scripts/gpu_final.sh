@@ -9,6 +9,7 @@ timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -5 | t
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -4 | tee gpurun_out/smoke.log
 timeout 300 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-400
 tail -3 gpurun_out/bench.err
+for a in uit_xxxs uit_xxs; do timeout 120 python bench.py --arch $a --steps 50 --warmup 5 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_$a.json; done
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json | cut -c1-300
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:encoder_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_encoder $B > gpurun_out/ncu_enc.log 2>&1; echo "ncu enc $?"
