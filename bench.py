@@ -352,7 +352,11 @@ def run_b200(args):
             return model.encode(db_w, mp_w)
 
         ms_sl = {}
-        for name, fn in (("per_window_frontend", per_window), ("shared_stft", lambda: model.forward_sliding(stream, hop=hop_s))):
+        def shared_stft():      # interior STFT frames computed once for the stream (uitk_logmel_sliding); rank-local: no collective,
+            db_w, mp_w = model.front_end.logmel_sliding(stream, 16000, hop_s)      # the other ranks have already left
+            return model.encode(db_w, mp_w)
+
+        for name, fn in (("per_window_frontend", per_window), ("shared_stft", shared_stft)):
             for _ in range(2):
                 y_sl = fn()
             torch.cuda.synchronize()
