@@ -81,11 +81,86 @@ def test_encoder_pack_tensor_order_and_size(lib):
     assert lib.uitk_encoder_blob_bytes(C.byref(bad)) == 0 and b"outputdim" in lib.uitk_last_error()
 
 
+def _bf16_to_f32(u16: np.ndarray) -> np.ndarray:
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def test_encoder_pack_bf16_section_layout(lib):
+    """The tensor-core blob: weights as K-major core-matrix tiles in the kernel's consumption order, every Linear bias as a
+    [N x 8] bf16 bias tile whose hi + mid + lo columns reproduce the fp32 value (csrc/pack.cu, csrc/encoder_tc.cu)."""
+    from uit_mobile_b200 import _native as N
+    depth = 4
+    names = N.encoder_tensor_names(depth)
+    sd = H.make_state_dict("uit_xxxs", "trained")
+    host = [sd[n].detach().to(torch.float32).contiguous() for n in names]
+    ptrs = (C.c_void_p * len(host))(*[h.data_ptr() for h in host])
+    cfg32, cfg16 = N.EncoderCfg(depth, 537, 6, 0), N.EncoderCfg(depth, 537, 6, 1)
+    n32, n16 = lib.uitk_encoder_blob_bytes(C.byref(cfg32)), lib.uitk_encoder_blob_bytes(C.byref(cfg16))
+    patch_bytes, qkv_half, qkv_bias, proj, tile, btile, fc1_bias = 4 * 16384, 96 * 64 * 2, 96 * 16, 128 * 32 * 2, 16384, 2048, 1024
+    block_bytes = 2 * qkv_half + qkv_bias + proj + btile + 6 * (tile + fc1_bias) + 6 * tile + btile
+    assert n16 - n32 == patch_bytes + depth * block_bytes
+    blob = np.zeros(n16, np.uint8)
+    assert lib.uitk_pack_encoder(C.byref(cfg16), ptrs, blob.ctypes.data, n16) == 0, lib.uitk_last_error()
+    sec = blob[n32:].view(np.uint16)                          # bf16 section (the fp32 section is padded to 1 KB, as n32 is)
+
+    def kmajor(off_bytes, n, k):                              # [(k/8), n, 8] -> [n, k]
+        t = sec[off_bytes // 2: off_bytes // 2 + n * k].reshape(k // 8, n, 8)
+        return _bf16_to_f32(t.transpose(1, 0, 2).reshape(n, k))
+
+    def bias_tile(off_bytes, n):
+        t = _bf16_to_f32(sec[off_bytes // 2: off_bytes // 2 + n * 8].reshape(n, 8))
+        assert (t[:, 3:] == 0).all()
+        return t[:, 0].astype(np.float64) + t[:, 1] + t[:, 2]
+
+    bf = lambda w: _bf16_to_f32((w.numpy().view(np.uint32) + 0x7FFF + ((w.numpy().view(np.uint32) >> 16) & 1) >> 16).astype(np.uint16))
+    # patch weight: 4 K-quarters of [128 x 64]
+    pw = sd["patch_embed.proj.weight"].reshape(128, 256)
+    for c in range(4):
+        np.testing.assert_array_equal(kmajor(c * 16384, 128, 64), bf(pw[:, c * 64:(c + 1) * 64].contiguous()))
+    # block 1 (second block): LayerNorm affine folded into qkv / fc1, biases as tiles
+    i = 1
+    off = patch_bytes + i * block_bytes
+    g1, b1 = sd[f"blocks.{i}.norm1.weight"].double(), sd[f"blocks.{i}.norm1.bias"].double()
+    wq, bq = sd[f"blocks.{i}.attn.qkv.weight"].double(), sd[f"blocks.{i}.attn.qkv.bias"].double()
+    np.testing.assert_allclose(kmajor(off, 96, 64), (wq * g1)[:, :64].float().numpy(), rtol=2 ** -8, atol=1e-30)
+    np.testing.assert_allclose(bias_tile(off + qkv_half, 96), (bq + wq @ b1).numpy(), rtol=1e-6, atol=1e-7)
+    off += 2 * qkv_half + qkv_bias
+    np.testing.assert_array_equal(kmajor(off, 128, 32), bf(sd[f"blocks.{i}.attn.proj.weight"]))
+    np.testing.assert_allclose(bias_tile(off + proj, 128), sd[f"blocks.{i}.attn.proj.bias"].double().numpy(), rtol=1e-6, atol=1e-7)
+    off += proj + btile
+    # MLP slots in issue order: fc1[0] fc1[1] | fc1[2] fc2[0] | fc1[3] fc2[1] | fc1[4] fc2[2] | fc1[5] fc2[3] | fc2[4] | fc2[5]
+    g2, b2 = sd[f"blocks.{i}.norm2.weight"].double(), sd[f"blocks.{i}.norm2.bias"].double()
+    w1, bb1 = sd[f"blocks.{i}.mlp.fc1.weight"].double(), sd[f"blocks.{i}.mlp.fc1.bias"].double()
+    w2, bb2 = sd[f"blocks.{i}.mlp.fc2.weight"], sd[f"blocks.{i}.mlp.fc2.bias"].double()
+    order = [("fc1", 0), ("fc1", 1)] + [x for c in range(1, 6) for x in ((("fc1", c + 1),) if c < 5 else ()) + (("fc2", c - 1),)] + [("fc2", 5)]
+    assert [o for o in order if o[0] == "fc1"] == [("fc1", c) for c in range(6)] and len(order) == 12
+    for kind, c in order:
+        if kind == "fc1":
+            np.testing.assert_allclose(kmajor(off, 64, 128), (w1 * g2)[64 * c:64 * c + 64].float().numpy(), rtol=2 ** -8, atol=1e-30)
+            np.testing.assert_allclose(bias_tile(off + tile, 64), (bb1 + w1 @ b2)[64 * c:64 * c + 64].numpy(), rtol=1e-6, atol=1e-7)
+            off += tile + fc1_bias
+        else:
+            np.testing.assert_array_equal(kmajor(off, 128, 64), bf(w2[:, 64 * c:64 * c + 64].contiguous()))
+            off += tile
+            if c == 0:
+                np.testing.assert_allclose(bias_tile(off, 128), bb2.numpy(), rtol=1e-6, atol=1e-7)
+                off += btile
+    assert off == patch_bytes + (i + 1) * block_bytes
+
+
 def test_launch_entry_points_validate_before_touching_cuda(lib):
     assert lib.uitk_logmel(None, 1, 16000, 16000, None, None, None, None, None) == -1
     one = C.c_float(0)
     p = C.addressof(one)
     assert lib.uitk_logmel(p, 1, 100, 100, p, p, p, None, None) == -1 and b"reflect" in lib.uitk_last_error()
+    # sliding windows: hop / window must be multiples of the STFT hop, the stream at least one window long
+    buf = np.zeros(64, np.float32)
+    p = (buf.ctypes.data + 15) // 16 * 16                       # 16-byte aligned dummy pointer (never dereferenced)
+    assert lib.uitk_logmel_sliding(p, 160000, 16000, 1000, p, p, p, None, p, 1 << 20, None) == -1 and b"multiple" in lib.uitk_last_error()
+    assert lib.uitk_logmel_sliding(p, 160000, 16001, 1600, p, p, p, None, p, 1 << 20, None) == -1
+    assert lib.uitk_logmel_sliding(p, 8000, 16000, 1600, p, p, p, None, p, 1 << 20, None) == -1 and b"shorter" in lib.uitk_last_error()
+    assert lib.uitk_logmel_sliding_workspace_bytes(160000) == 64 * 1001 * 4
+    assert lib.uitk_logmel_sliding(p, 160000, 16000, 1600, p, p, p, None, p, 16, None) < 0 and b"workspace" in lib.uitk_last_error()
 
 
 def test_module_contract():
