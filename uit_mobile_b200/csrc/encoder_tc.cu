@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     };
 
     const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
-    const int tokens = p.tokens, t_n = p.t_n;
+    const int tokens = p.tokens;          // 24: the kernel is only launched for the 24-token geometry (run_encoder_tc)
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int rr0 = tile * p.G;
@@ -566,7 +566,6 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           // ---------- tensor-core attention: S_h = Q_h K_h^T and O_h = P_h V_h on tcgen05, softmax straight from TMEM ----------
           const bool valid = r < rows_valid;
           const int g = valid ? r / 24 : 0;
-          const int cbase = g * 24;                                   // this row's keys = S columns [cbase, cbase + 24)
           {   // qkv (+bias) -> bf16 operands.  hsel 0 holds q(32) k_h0(16); hsel 1 holds k_h1(16) v(32)
             float v[32], w[16];
             tmem_ld32(tacc + hsel * 48, v);
