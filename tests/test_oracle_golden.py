@@ -95,3 +95,19 @@ def test_trace_matches():
     tr = O.forward_trace(sd, torch.from_numpy(INPUTS["noise"][:2]))
     for k in ("db", "bn", "tokens", "blocks", "features", "probs"):
         np.testing.assert_allclose(tr[k].numpy(), z[k], atol=2e-5, rtol=0)
+
+
+def test_sliding_window_premise_interior_frames_are_stream_frames():
+    """Premise of uitk_logmel_sliding, checked on the reference-pinned oracle: frame t in [2, T-2) of the window
+    starting at sample w*hop never touches the window's reflect padding, so it equals frame w*hop/160 + t of the stream taken as
+    one clip - bit for bit; the 4 edge frames differ (per-window reflect padding)."""
+    sd = H.make_state_dict("uit_xxxs")
+    win, fb = sd["front_end.0.spectrogram.window"], sd["front_end.0.mel_scale.fb"]
+    n, hop = 16000 * 3 + 777, 1600
+    stream = torch.from_numpy(H.noise_clips(1, n, seed=9)[0])
+    mel_w = O.mel_power(O.power_spectrogram(stream.unfold(0, 16000, hop).contiguous(), win), fb)      # [W, 64, 101]
+    mel_s = O.mel_power(O.power_spectrogram(stream[None], win), fb)[0]                                # [64, U]
+    r = hop // 160
+    for w in range(mel_w.shape[0]):
+        assert torch.equal(mel_w[w][:, 2:99], mel_s[:, w * r + 2: w * r + 99])
+    assert not torch.equal(mel_w[1][:, :2], mel_s[:, r: r + 2])          # edge frames are NOT shared
