@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libuitk.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]      # no --use_fast_math: fp32 parity paths need IEEE div/sqrt
 
 
 def sources():
@@ -35,7 +35,7 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags = list(FLAGS)
     if os.environ.get("UITK_TRACE"):        # in-kernel stage timeline of the tensor-core encoder (profiling builds only)
         flags.append("-DUITK_TRACE")
     objs = []
