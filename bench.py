@@ -356,6 +356,8 @@ def run_b200(args):
             db_w, mp_w = model.front_end.logmel_sliding(stream, 16000, hop_s)      # the other ranks have already left
             return model.encode(db_w, mp_w)
 
+        if world == 1:          # the public entry point (it all-reduces the max word when the model is sharded)
+            shared_stft = lambda: model.forward_sliding(stream, hop=hop_s)
         for name, fn in (("per_window_frontend", per_window), ("shared_stft", shared_stft)):
             for _ in range(2):
                 y_sl = fn()
