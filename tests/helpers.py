@@ -27,8 +27,9 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
     """A full UiT state_dict (same keys/shapes/dtypes as the reference).
 
     kind='init'    ~ the reference's default init statistics (flat outputs, BN = identity).
-    kind='trained' ~ weights with trained-like scale so that no branch is trivially identity and the 537
-                     probabilities spread over (0, 1) (top-5 comparisons become meaningful).
+    kind='trained' ~ weights with trained-like scale so that no branch is trivially identity, and a
+                     sparse-activation head (a handful of classes above 0.1 per clip, the rest near sigmoid(-6)):
+                     literal top-5 comparisons are meaningful on it.
     """
     from oracle import uit_oracle as O     # only for the analytic window / mel filterbank buffers
     depth = DEPTH[arch]
@@ -74,8 +75,22 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
     sd["norm.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
     sd["outputlayer.0.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
     sd["outputlayer.0.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
-    sd["outputlayer.1.weight"] = lin(outputdim, D, 0.25 if tr else 0.02)
-    sd["outputlayer.1.bias"] = vec(outputdim, -1.0 if tr else 0.0, 1.0 if tr else 0.0)
+    if tr:
+        # Sparse-activation head, like a trained tagger (the reference's own known answers, README.md:85-116, have a
+        # handful of classes above 0.1: 0.4467 / 0.3263 / 0.1718 ...): ~40 "active" classes with large-norm rows around a
+        # bias of -4, every other class pinned near sigmoid(-6).  Top-5 gaps are then >> the bf16 noise, so LITERAL top-5
+        # equality is a meaningful check (round-1 verdict: the old std-0.25 / bias -1 head saturated ~50 classes).
+        n_act = max(5, (40 * outputdim) // 537)
+        scale = np.full((outputdim, 1), 0.04)
+        bias = np.full(outputdim, -6.0)
+        act = g.permutation(outputdim)[:n_act]
+        scale[act] = 0.22
+        bias[act] = -4.0
+        sd["outputlayer.1.weight"] = _t(g.standard_normal((outputdim, D)) * scale)
+        sd["outputlayer.1.bias"] = _t(bias + g.standard_normal(outputdim) * 0.3)
+    else:
+        sd["outputlayer.1.weight"] = lin(outputdim, D, 0.02)
+        sd["outputlayer.1.bias"] = vec(outputdim, 0.0, 0.0)
     return sd
 
 
@@ -105,6 +120,40 @@ def samples_int16() -> np.ndarray:
     """The reference's 11 sample clips (int16), zero-padded to 16384, plus their true lengths."""
     z = load_golden("samples_int16.npz")
     return z["pcm"], z["length"], [str(s) for s in z["names"]]
+
+
+def logits_of(p: np.ndarray) -> np.ndarray:
+    """log(p / (1 - p)) in float64 (the model outputs sigmoid probabilities, Q1)."""
+    p = np.clip(p.astype(np.float64), 1e-12, 1.0 - 1e-12)
+    return np.log(p) - np.log1p(-p)
+
+
+def topk_report(ref: np.ndarray, got: np.ndarray, k: int = 5, eps_logit: float = 0.05) -> Dict[str, float]:
+    """LITERAL top-k check in logit space.  A clip is *decisive* when the reference's k-th and (k+1)-th logits are more
+    than 2*eps_logit apart: the top-k SET of an implementation whose logits are within eps_logit must then be identical.
+    Returns the max |d logit| (over classes whose reference probability is representable: 1e-6 < p < 1 - 1e-6), the
+    fraction of decisive clips, the fraction of decisive clips whose literal top-k set matches (must be 1.0), the fraction
+    of ALL clips whose literal top-k set matches, and the mean size of the strict `must` set (reference classes more
+    than 2*eps_logit above the k-th): a vacuous check shows up as decisive == 0 / must == 0."""
+    zr, zg = logits_of(ref), logits_of(got)
+    ok = (ref > 1e-6) & (ref < 1 - 1e-6)
+    dz = float(np.abs(zr - zg)[ok].max()) if ok.any() else 0.0
+    decisive = match_dec = match_all = 0
+    must_sizes = []
+    for r, o in zip(zr, zg):
+        srt = np.sort(r)
+        kth, nxt = srt[-k], srt[-k - 1]
+        top_r = set(np.argsort(-r, kind="stable")[:k])
+        top_o = set(np.argsort(-o, kind="stable")[:k])
+        same = top_r == top_o
+        match_all += same
+        must_sizes.append(int((r > kth + 2 * eps_logit).sum()))
+        if kth - nxt > 2 * eps_logit:
+            decisive += 1
+            match_dec += same
+    n = len(zr)
+    return {"max_dlogit": dz, "decisive_frac": decisive / n, "decisive_match_frac": (match_dec / decisive) if decisive else 0.0,
+            "literal_match_frac": match_all / n, "must_mean": float(np.mean(must_sizes)), "n": n}
 
 
 def tie_aware_topk_equal(ref: np.ndarray, got: np.ndarray, k: int = 5, eps: float = 1e-3) -> bool:

@@ -2,10 +2,13 @@
 stream against the reference trace, and scores against the reference goldens.
 
 Stated tolerance (north_star: "logits within a stated bf16 tolerance with identical top-5"): bf16 GEMM operands,
-fp32 accumulate / residual / LayerNorm / softmax.  |d prob| <= 1e-3 for the reference-like 'init' weights (measured
-3.5e-4 .. 4.7e-4) and <= 2.5e-2 for the deliberately large-magnitude 'trained' weight set (measured 6.7e-3 .. 1.6e-2:
-its head weights have std 0.25, i.e. logit std ~3, which amplifies the ~0.4 % bf16 operand noise of the features);
-top-5 identical up to ties within 2*eps of the reference 5th value."""
+fp32 accumulate / residual / LayerNorm / softmax.  ONE bound per weight set, in logits and in probabilities:
+  'init'    (reference-like init statistics, flat 0.3-0.7 outputs):  |d logit| <= 5e-3, |d prob| <= 1e-3; top-5 compared
+            tie-aware (literal top-5 equality is unattainable on flat outputs even in TF32: SURVEY 7.2);
+  'trained' (large-magnitude blocks + sparse-activation head, helpers.make_state_dict): |d logit| <= EPS_LOGIT['trained'],
+            |d prob| <= TOL['trained']; LITERAL top-5 set equality on every clip whose reference 5th / 6th logits are more
+            than 2*eps apart, with the assertion that the strict `must` set is non-empty on >= 90 % of the clips (the check
+            cannot go vacuous)."""
 import numpy as np
 import pytest
 import torch
@@ -16,6 +19,7 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = {"init": 1e-3, "trained": 2.5e-2}
+EPS_LOGIT = {"init": 5e-3, "trained": 0.1}
 
 
 def pack_kmajor(w: torch.Tensor) -> torch.Tensor:
@@ -94,23 +98,46 @@ def test_bf16_residual_stream_vs_reference_trace(depth):
     assert err <= 0.02 * np.abs(ref).max() + 0.02
 
 
+def _golden_inputs():
+    pcm, length, _ = H.samples_int16()
+    x16 = np.zeros((len(pcm), 16000), np.float32)
+    for i in range(len(pcm)):
+        n = min(16000, int(length[i]))
+        x16[i, :n] = pcm[i, :n].astype(np.float32) / 32768.0
+    return {"samples16k": x16, "noise": H.noise_clips(32), "adversarial": H.adversarial_batch(), "short2400": H.noise_clips(3, 2400, seed=11),
+            "short14336": H.noise_clips(3, 14336, seed=12), "len16160": H.noise_clips(2, 16160, seed=14),
+            "long10s": H.noise_clips(2, 160000, seed=13)}
+
+
 @pytest.mark.parametrize("arch", H.ARCHS)
 @pytest.mark.parametrize("kind", ["init", "trained"])
 def test_bf16_scores_vs_reference_golden(arch, kind):
+    """The shipped default path against the REAL reference's outputs on every golden input set, BASELINE config 1
+    (samples/*.wav as a 1 s batch and at native length) included."""
     g = H.load_golden("probs.npz")
     m = _model(arch, kind, "bf16")
-    inputs = {"noise": H.noise_clips(32), "adversarial": H.adversarial_batch(), "short2400": H.noise_clips(3, 2400, seed=11),
-              "short14336": H.noise_clips(3, 14336, seed=12), "long10s": H.noise_clips(2, 160000, seed=13)}
-    worst = 0.0
-    for name, x in inputs.items():
+    pcm, length, _ = H.samples_int16()
+    refs, gots = [], []
+    for name, x in _golden_inputs().items():
         y = m(torch.from_numpy(x).to(DEV)).cpu().numpy()
         ref = g[f"{arch}/{kind}/{name}"]
-        assert y.shape == ref.shape
-        assert np.isfinite(y).all()
-        worst = max(worst, float(np.abs(y - ref).max()))
-        assert H.tie_aware_topk_equal(ref, y, 5, eps=TOL[kind]), name
-    print(f"{arch}/{kind}: max|d prob| = {worst:.2e}")
+        assert y.shape == ref.shape and np.isfinite(y).all(), name
+        refs.append(ref); gots.append(y)
+    nat = np.stack([m(torch.from_numpy(pcm[i, : length[i]].astype(np.float32)[None] / 32768.0).to(DEV)).cpu().numpy()[0]
+                    for i in range(len(pcm))])
+    refs.append(g[f"{arch}/{kind}/samples_native"]); gots.append(nat)
+    ref, got = np.concatenate(refs), np.concatenate(gots)
+    worst = float(np.abs(got - ref).max())
+    rep = H.topk_report(ref, got, 5, eps_logit=EPS_LOGIT[kind])
+    print(f"{arch}/{kind}: max|d prob| = {worst:.2e}  {rep}")
     assert worst <= TOL[kind], worst
+    assert rep["max_dlogit"] <= EPS_LOGIT[kind], rep
+    if kind == "trained":
+        assert rep["decisive_match_frac"] == 1.0, rep          # literal top-5 wherever the reference is decisive
+        must_nonempty = np.mean([(H.logits_of(r) > np.sort(H.logits_of(r))[-5] + 2 * EPS_LOGIT[kind]).any() for r in ref])
+        assert must_nonempty >= 0.9 and rep["decisive_frac"] >= 0.4, (must_nonempty, rep)   # never vacuous
+    else:
+        assert H.tie_aware_topk_equal(ref, got, 5, eps=TOL[kind])
 
 
 def test_bf16_matches_oracle_on_large_seeded_batch_with_ragged_tail():
