@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 103
+#define UITK_VERSION 200
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
@@ -53,6 +53,15 @@ extern "C" {
 /* Encoder arithmetic. */
 #define UITK_PREC_FP32 0   /* fp32 CUDA-core GEMMs (validation path) */
 #define UITK_PREC_BF16 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/residual/LN/softmax */
+
+/* UITBase variants behind the same API (models/uit.py:89-178, 181-203, 389-412). */
+#define UITK_ATTN_BNECK 0  /* BNeckAttention: qkv 128->96, 2 heads x 16, proj 32->128 (uit.py:89-122) */
+#define UITK_ATTN_FULL 1   /* Attention: qkv 128->384, 2 heads x 64, proj 128->128 (uit.py:124-178, causal=False) */
+#define UITK_ACT_RELU 0
+#define UITK_ACT_GELU 1    /* nn.GELU (exact erf), the UITBase default (uit.py:338) */
+#define UITK_POOL_MEAN 0   /* mean over tokens (uit.py:402-404) */
+#define UITK_POOL_TOKEN 1  /* cls token + token_pos_embed prepended, head on token 0 (uit.py:389-392, 399-401) */
+#define UITK_POOL_DM 2     /* mean over frequency, head per time step, mean of the scores (uit.py:405-412) */
 
 UITK_API int uitk_version(void);
 UITK_API const char* uitk_last_error(void);
@@ -119,17 +128,25 @@ typedef struct {
   int depth;          /* 12 / 6 / 4 */
   int outputdim;      /* 537 */
   int grid_t;         /* time_pos_embed length (6 for target_length 102) */
-  int precision;      /* UITK_PREC_* */
+  int precision;      /* UITK_PREC_* : the tensor-core megakernel runs the UiT-XS/XXS/XXXS configuration
+                         (BNECK + RELU + MEAN); every other variant runs on the fp32 CUDA-core kernels */
+  int attention;      /* UITK_ATTN_* */
+  int act;            /* UITK_ACT_* */
+  int pooling;        /* UITK_POOL_* */
+  int reserved;       /* 0 */
 } uitk_encoder_cfg;
 
 UITK_API int uitk_encoder_num_tensors(int depth);
 UITK_API const char* uitk_encoder_tensor_name(int depth, int index);   /* state_dict key of h_tensors[index] */
+/* tokens per crop incl. the cls token of UITK_POOL_TOKEN */
+UITK_API int uitk_tokens_total(const uitk_encoder_cfg* cfg, int64_t T, int target_length);
 UITK_API size_t uitk_encoder_blob_bytes(const uitk_encoder_cfg* cfg);
 UITK_API int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* h_tensors, void* h_blob, size_t blob_bytes);
 
 /* ---- encoder ----------------------------------------------------------------------------------------------------
  * Replaces init_bn + crop loop + forward_features + forward_head (models/uit.py:460-492, 379-412, 89-122,
- * 181-248) for pooling='mean', BNeckAttention, ReLU MLP.
+ * 181-248).  UiT-XS/XXS/XXXS configuration (pooling='mean', BNeckAttention, ReLU MLP) on the tcgen05 megakernel when
+ * cfg->precision == UITK_PREC_BF16; full Attention / GELU / pooling 'token' | 'dm' on the fp32 CUDA-core kernels.
  *   d_db        [B, 64, T] un-clamped dB from uitk_logmel; the clamp with *d_max_pow is fused into the load
  *   d_probs     [B, outputdim] sigmoid scores, crops reduced by mean (eval_avg 0) or max (1)
  *   workspace   uitk_encoder_workspace_bytes(cfg, B, T, target_length) bytes, 256-B aligned */
@@ -137,6 +154,33 @@ UITK_API size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_
 UITK_API int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
                  int target_length, int eval_avg, const uint32_t* d_max_pow, float* d_probs,
                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Conditional exact re-run for callers that encoded SPECULATIVELY with a cutoff that was not yet batch-global (a rank's
+ * local maximum while the all-reduce(MAX) of the word is still in flight; models/uit.py forward with a process group).
+ * Same arguments as uitk_encoder plus three device words; every kernel of the launch decides ON THE DEVICE whether
+ * anything could differ and returns immediately if not (no host synchronisation, no collective on the critical path):
+ *   re-run  <=>  *d_max_used != *d_max_pow  and  dB(*d_min_pow) < dB(*d_max_pow) - 120
+ * i.e. the speculative cutoff was lower than the true one AND some value of this call's input lies below the true cutoff.
+ * Otherwise no value was (or would have been) clamped and the speculative scores are exactly the reference's.
+ * Tensor-core configuration only (returns UITK_EINVAL for fp32 / variant configurations: encode after the all-reduce). */
+UITK_API int uitk_encoder_fixup(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
+                       int target_length, int eval_avg, const uint32_t* d_max_pow, const uint32_t* d_max_used,
+                       const uint32_t* d_min_pow, float* d_probs, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- forward_features / forward_head (models/uit.py:379-412) as separate entry points -----------------------------
+ * The reference exposes both methods; uitk_encoder fuses them.  These two keep the method-level contract:
+ *   uitk_forward_features: d_spec [B, 64, T] = the ALREADY NORMALISED spectrogram the reference passes in (front_end +
+ *       init_bn applied by the caller, e.g. through uitk_logmel / uitk_clamp_db / uitk_init_bn), T <= 16*grid_t + 15
+ *       -> d_tokens [B, N, 128] after the final LayerNorm, N = 4 * ((T - 16)/16 + 1) (+1 cls token for UITK_POOL_TOKEN).
+ *   uitk_forward_head: d_tokens [B, N, 128] -> d_probs [B, outputdim] (pooling per cfg, LayerNorm 1e-5, Linear, sigmoid).
+ *       For UITK_POOL_DM the time-patch count is N / 4. */
+UITK_API int uitk_init_bn(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
+                          float* d_out, void* stream);
+UITK_API size_t uitk_forward_features_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T);
+UITK_API int uitk_forward_features(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_spec, int64_t B, int64_t T,
+                          float* d_tokens, void* d_workspace, size_t workspace_bytes, void* stream);
+UITK_API int uitk_forward_head(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_tokens, int64_t B,
+                      int n_tokens, float* d_probs, void* stream);
 
 /* Debug/validation taps (tests only): copy of the token activations [B*crops*tokens, 128] after patch embed
  * (stage 0) or after block i (stage i+1) is left in the workspace at this byte offset after uitk_encoder. */

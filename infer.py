@@ -37,6 +37,8 @@ def main() -> int:
 
     if args.model in U.models.PRETRAINED_CHECKPOINTS:
         entry = U.models.PRETRAINED_CHECKPOINTS[args.model]
+        if args.random_init:
+            torch.manual_seed(0)           # reproducible smoke weights (tests compare the printout with the oracle)
         model = entry["model"](precision=args.precision, **entry["model_kwargs"])
         if not args.random_init:
             sd = torch.hub.load_state_dict_from_url(entry["chkpt"], map_location="cpu")
@@ -44,7 +46,8 @@ def main() -> int:
     else:
         dump = torch.load(args.model, map_location="cpu")
         cfg = dump["config"]
-        model = getattr(U.models, cfg["model"])(outputdim=537, precision=args.precision, **cfg.get("model_args", {}))
+        # inference.py:42-47: class count from the checkpoint's config (default 537), model_args required
+        model = getattr(U.models, cfg["model"])(outputdim=cfg.get("num_classes", 537), precision=args.precision, **cfg["model_args"])
         model.load_state_dict(dump["model"], strict=True)
     model = model.to("cuda:0").eval()
 

@@ -132,9 +132,11 @@ def patch_tokens(xn: Tensor, sd: Dict[str, Tensor]) -> Tensor:
 
 
 def attention(x: Tensor, sd: Dict[str, Tensor], i: int) -> Tensor:
-    """BNeckAttention (uit.py:89-122): inner dim 32, 2 heads x 16, scale = (128//2)**-0.5 = 0.125 (Q3)."""
+    """BNeckAttention (uit.py:89-122): inner dim 32, 2 heads x 16, scale = (128//2)**-0.5 = 0.125 (Q3); or the full
+    ``Attention`` (uit.py:124-178, causal=False): inner dim 128, 2 heads x 64, same scale.  Which one is read off the qkv
+    weight's shape ([96, 128] vs [384, 128])."""
     B, N, C = x.shape
-    inner = C // 4
+    inner = sd[f"blocks.{i}.attn.qkv.weight"].shape[0] // 3
     qkv = F.linear(x, sd[f"blocks.{i}.attn.qkv.weight"], sd[f"blocks.{i}.attn.qkv.bias"])
     qkv = qkv.reshape(B, N, 3, HEADS, inner // HEADS).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
@@ -144,17 +146,19 @@ def attention(x: Tensor, sd: Dict[str, Tensor], i: int) -> Tensor:
     return F.linear(o, sd[f"blocks.{i}.attn.proj.weight"], sd[f"blocks.{i}.attn.proj.bias"])
 
 
-def mlp(x: Tensor, sd: Dict[str, Tensor], i: int) -> Tensor:
-    """fc2(ReLU(fc1(x))) (uit.py:197-203; act_layer=nn.ReLU for all UiT archs, Q7)."""
-    h = F.relu(F.linear(x, sd[f"blocks.{i}.mlp.fc1.weight"], sd[f"blocks.{i}.mlp.fc1.bias"]))
+def mlp(x: Tensor, sd: Dict[str, Tensor], i: int, act: str = "relu") -> Tensor:
+    """fc2(act(fc1(x))) (uit.py:197-203; act_layer=nn.ReLU for all UiT archs, Q7; nn.GELU (exact erf) is the UITBase
+    default, uit.py:338)."""
+    h = F.linear(x, sd[f"blocks.{i}.mlp.fc1.weight"], sd[f"blocks.{i}.mlp.fc1.bias"])
+    h = F.relu(h) if act == "relu" else F.gelu(h)
     return F.linear(h, sd[f"blocks.{i}.mlp.fc2.weight"], sd[f"blocks.{i}.mlp.fc2.bias"])
 
 
-def block(x: Tensor, sd: Dict[str, Tensor], i: int) -> Tensor:
+def block(x: Tensor, sd: Dict[str, Tensor], i: int, act: str = "relu") -> Tensor:
     """Pre-norm residual block (uit.py:245-248); LayerScale/DropPath are Identity."""
     p = f"blocks.{i}."
     x = x + attention(F.layer_norm(x, (EMBED,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS_BLOCK), sd, i)
-    x = x + mlp(F.layer_norm(x, (EMBED,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS_BLOCK), sd, i)
+    x = x + mlp(F.layer_norm(x, (EMBED,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS_BLOCK), sd, i, act)
     return x
 
 
@@ -162,33 +166,49 @@ def depth_of(sd: Dict[str, Tensor]) -> int:
     return 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
 
 
-def features(xn: Tensor, sd: Dict[str, Tensor], trace: Optional[list] = None) -> Tensor:
-    """forward_features (uit.py:379-396), pooling='mean' (no cls token, Q4)."""
+def features(xn: Tensor, sd: Dict[str, Tensor], trace: Optional[list] = None, act: str = "relu", pooling: str = "mean") -> Tensor:
+    """forward_features (uit.py:379-396).  pooling='token' prepends cls_token + token_pos_embed (uit.py:389-392); the
+    UiT archs use pooling='mean' (no cls token, Q4)."""
     x = patch_tokens(xn, sd)
+    if pooling == "token":
+        cls = sd["cls_token"].expand(x.shape[0], -1, -1) + sd["token_pos_embed"]
+        x = torch.cat((cls, x), dim=1)
     if trace is not None:
         trace.append(x.clone())
     for i in range(depth_of(sd)):
-        x = block(x, sd, i)
+        x = block(x, sd, i, act)
         if trace is not None:
             trace.append(x.clone())
     return F.layer_norm(x, (EMBED,), sd["norm.weight"], sd["norm.bias"], LN_EPS_BLOCK)
 
 
-def head(x: Tensor, sd: Dict[str, Tensor]) -> Tensor:
-    """forward_head, pooling='mean' (uit.py:402-404): mean over tokens, LN(1e-5), Linear, sigmoid (Q1)."""
-    x = x.mean(1)
+def _outputlayer(x: Tensor, sd: Dict[str, Tensor]) -> Tensor:
     x = F.layer_norm(x, (EMBED,), sd["outputlayer.0.weight"], sd["outputlayer.0.bias"], LN_EPS_HEAD)
-    return F.linear(x, sd["outputlayer.1.weight"], sd["outputlayer.1.bias"]).sigmoid()
+    return F.linear(x, sd["outputlayer.1.weight"], sd["outputlayer.1.bias"])
 
 
-def encode(db: Tensor, sd: Dict[str, Tensor], target_length: int = 102, eval_avg: str = "mean") -> Tensor:
+def head(x: Tensor, sd: Dict[str, Tensor], pooling: str = "mean") -> Tensor:
+    """forward_head (uit.py:398-412).  'mean': mean over tokens, LN(1e-5), Linear, sigmoid (Q1); 'token': the cls row;
+    'dm': unpack (f t), mean over frequency, head + sigmoid per time step, mean of the scores."""
+    if pooling == "token":
+        return _outputlayer(x[:, 0], sd).sigmoid()
+    if pooling == "mean":
+        return _outputlayer(x.mean(1), sd).sigmoid()
+    if pooling == "dm":
+        B, N, D = x.shape
+        return _outputlayer(x.reshape(B, 4, N // 4, D).mean(1), sd).sigmoid().mean(1)
+    raise ValueError(pooling)
+
+
+def encode(db: Tensor, sd: Dict[str, Tensor], target_length: int = 102, eval_avg: str = "mean", act: str = "relu",
+           pooling: str = "mean") -> Tensor:
     """BatchNorm + crop loop + features + head on an already computed log-mel (uit.py:460-492)."""
     xn = init_bn(db, sd)
     T = xn.shape[-1]
     starts = crop_starts(T, target_length)
     if T <= target_length:
-        return head(features(xn, sd), sd)
-    outs = [head(features(xn[..., s:s + target_length], sd), sd) for s in starts]
+        return head(features(xn, sd, None, act, pooling), sd, pooling)
+    outs = [head(features(xn[..., s:s + target_length], sd, None, act, pooling), sd, pooling) for s in starts]
     y = torch.stack(outs, -1)
     if eval_avg == "mean":
         return y.mean(-1)
@@ -199,12 +219,12 @@ def encode(db: Tensor, sd: Dict[str, Tensor], target_length: int = 102, eval_avg
 
 @torch.no_grad()
 def forward(sd: Dict[str, Tensor], wav: Tensor, target_length: int = 102, eval_avg: str = "mean",
-            cutoff_max_db: Optional[Tensor] = None) -> Tensor:
+            cutoff_max_db: Optional[Tensor] = None, act: str = "relu", pooling: str = "mean") -> Tensor:
     """UITBase.forward, eval branch (uit.py:452-493).  wav [B, L] fp32 -> [B, outputdim] probabilities."""
     if wav.dim() != 2:
         raise ValueError("expected a [B, L] waveform batch")
     db = logmel(wav, sd["front_end.0.spectrogram.window"], sd["front_end.0.mel_scale.fb"], cutoff_max_db)
-    return encode(db, sd, target_length, eval_avg)
+    return encode(db, sd, target_length, eval_avg, act, pooling)
 
 
 @torch.no_grad()

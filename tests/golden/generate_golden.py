@@ -143,6 +143,25 @@ def main():
             print(arch, kind, "ok")
     np.savez_compressed(os.path.join(HERE, "probs.npz"), **out)
 
+    # ---- UITBase variants: full Attention, GELU, pooling 'token' / 'dm', through the reference's own factories
+    vout = {}
+    for name, (depth, attention, act, pooling) in H.VARIANTS.items():
+        for kind in ("init", "trained"):
+            sd = H.make_state_dict(name, kind)
+            model = H.build_variant(ref_models, name)
+            assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(v.shape)) for k, v in model.state_dict().items()], name
+            model.load_state_dict(sd, strict=True)
+            model.eval()
+            for k, x in H.variant_inputs().items():
+                with torch.no_grad():
+                    r = model(torch.from_numpy(x))
+                o = O.forward(sd, torch.from_numpy(x), act=act, pooling=pooling)
+                err = float((r - o).abs().max())
+                assert err <= 2e-6, f"oracle != reference: {name}/{kind}/{k}: {err}"
+                vout[f"{name}/{kind}/{k}"] = r.numpy()
+            print(name, kind, "ok")
+    np.savez_compressed(os.path.join(HERE, "probs_variants.npz"), **vout)
+
     # ---- per-stage trace (kernel bring-up aid): reference module pieces, xxxs/trained, 2 noise clips
     sd = H.make_state_dict("uit_xxxs", "trained")
     model = ref_models.uit_xxxs(outputdim=537, target_length=102); model.load_state_dict(sd); model.eval()

@@ -22,8 +22,17 @@ def _t(a) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
 
+# UITBase variants beyond the three UiT archs: name -> (depth, attention_type, act, pooling)
+VARIANTS = {
+    "h128_d4_m3": (4, "Attention", "gelu", "mean"),                 # audio_transformer_h128_d4_m3 (uit.py:531-545)
+    "h128_d4_m3_relu_token": (4, "Attention", "relu", "token"),     # audio_transformer_h128_d4_m3_relu(pooling='token')
+    "uit_xxxs_dm": (4, "BNeckAttention", "relu", "dm"),             # uit_xxxs(pooling='dm')
+    "uit_xxxs_gelu_token": (4, "BNeckAttention", "gelu", "token"),  # uit_xxxs(act_layer=nn.GELU, pooling='token')
+}
+
+
 def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: int = OUTPUTDIM,
-                    grid_t: int = 6) -> Dict[str, torch.Tensor]:
+                    grid_t: int = 6, attention: str = "BNeckAttention") -> Dict[str, torch.Tensor]:
     """A full UiT state_dict (same keys/shapes/dtypes as the reference).
 
     kind='init'    ~ the reference's default init statistics (flat outputs, BN = identity).
@@ -32,8 +41,11 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
                      literal top-5 comparisons are meaningful on it.
     """
     from oracle import uit_oracle as O     # only for the analytic window / mel filterbank buffers
-    depth = DEPTH[arch]
-    g = np.random.Generator(np.random.PCG64([seed, depth, 0 if kind == "init" else 1]))
+    depth = DEPTH[arch] if arch in DEPTH else VARIANTS[arch][0]
+    if arch in VARIANTS:
+        attention = VARIANTS[arch][1]
+    full = attention == "Attention"
+    g = np.random.Generator(np.random.PCG64([seed, depth, 0 if kind == "init" else 1] + ([7] if full else [])))
     tr = kind == "trained"
 
     def lin(out_f, in_f, std):
@@ -44,7 +56,9 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
 
     D, H, I = 128, 384, 32
     sd: Dict[str, torch.Tensor] = {}
-    sd["cls_token"] = _t(g.standard_normal((1, 1, D)) * 1e-6)
+    if full:
+        I = D                      # Attention: qkv 128 -> 384, proj 128 -> 128
+    sd["cls_token"] = _t(g.standard_normal((1, 1, D)) * (0.3 if tr else 1e-6))
     sd["token_pos_embed"] = _t(g.standard_normal((1, D)) * 0.02)
     sd["time_pos_embed"] = _t(g.standard_normal((1, D, 1, grid_t)) * (0.3 if tr else 0.02))
     sd["freq_pos_embed"] = _t(g.standard_normal((1, D, 4, 1)) * (0.3 if tr else 0.02))
@@ -63,7 +77,7 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
         sd[p + "norm1.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
         sd[p + "attn.qkv.weight"] = lin(3 * I, D, 0.09 if tr else 0.02)
         sd[p + "attn.qkv.bias"] = vec(3 * I, 0.0, 0.05 if tr else 0.0)
-        sd[p + "attn.proj.weight"] = lin(D, I, 0.12 if tr else 0.02)
+        sd[p + "attn.proj.weight"] = lin(D, I, (0.06 if full else 0.12) if tr else 0.02)
         sd[p + "attn.proj.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
         sd[p + "norm2.weight"] = vec(D, 1.0, 0.1 if tr else 0.0)
         sd[p + "norm2.bias"] = vec(D, 0.0, 0.05 if tr else 0.0)
@@ -92,6 +106,22 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
         sd["outputlayer.1.weight"] = lin(outputdim, D, 0.02)
         sd["outputlayer.1.bias"] = vec(outputdim, 0.0, 0.0)
     return sd
+
+
+def build_variant(models_pkg, name: str, **kw):
+    """Construct VARIANTS[name] from a ``models`` package (the reference's or uit_mobile_b200's: same factories / kwargs)."""
+    import torch.nn as nn
+    depth, attention, act, pooling = VARIANTS[name]
+    act_layer = nn.ReLU if act == "relu" else nn.GELU
+    if attention == "Attention":
+        fac = getattr(models_pkg, f"audio_transformer_h128_d{depth}_m3" + ("_relu" if act == "relu" else ""))
+        return fac(outputdim=OUTPUTDIM, target_length=102, pooling=pooling, **kw)
+    return models_pkg.uit_xxxs(outputdim=OUTPUTDIM, target_length=102, pooling=pooling, act_layer=act_layer, **kw)
+
+
+def variant_inputs():
+    return {"noise": noise_clips(8), "adversarial": adversarial_batch(), "short14336": noise_clips(3, 14336, seed=12),
+            "len16160": noise_clips(2, 16160, seed=14), "long10s": noise_clips(2, 160000, seed=13)}
 
 
 def noise_clips(B: int, L: int = 16000, seed: int = 1234, amp: float = 0.1) -> np.ndarray:

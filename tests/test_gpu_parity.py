@@ -68,7 +68,7 @@ def assert_logmel_close(got, x, ref32):
 
 def test_library_loaded_is_in_tree():
     from uit_mobile_b200 import _native as N
-    assert N.lib().uitk_version() == 103
+    assert N.lib().uitk_version() == 200
     assert N.LIB_PATH.endswith("uit_mobile_b200/libuitk.so")
 
 
@@ -159,9 +159,11 @@ def test_fp32_encoder_block_trace(depth):
     m.load_state_dict(sub, strict=True)
     m = m.to(DEV).eval()
     x = torch.from_numpy(INPUTS["noise"][:2]).to(DEV)
-    m(x)
+    db, mp = m.front_end.logmel_unclamped(x)
+    ws = []
+    m.encode(db, mp, workspace_out=ws)
     torch.cuda.synchronize()
-    tok = m._last_workspace[: 2 * 24 * 128 * 4].view(torch.float32).view(2, 24, 128).cpu().numpy()
+    tok = ws[0][: 2 * 24 * 128 * 4].view(torch.float32).view(2, 24, 128).cpu().numpy()
     np.testing.assert_allclose(tok, z["blocks"][depth - 1], atol=2e-4, rtol=0)
 
 
@@ -290,6 +292,20 @@ def test_infer_cli_runs_like_inference_py(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("=====") == 4 and out.stdout.count("class ") + out.stdout.count("Keyword") >= 10
+    # the printed labels / scores are the oracle's top-5 for the same random-init weights (torch.manual_seed(0) in infer.py):
+    # every printed class must be admissible (within the bf16 tolerance of the reference's 5th score) and carry the right score
+    import re, uit_mobile_b200 as U
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in U.models.uit_xxxs(outputdim=537, target_length=102).state_dict().items()}
+    blocks = out.stdout.split("=====")[2::2]
+    for i, text in zip((0, 1), blocks):
+        ref = O.forward(sd, torch.from_numpy(pcm[i, : int(length[i])].astype(np.float32)[None] / 32768.0)).numpy()[0]
+        rows = re.findall(r"(?:Keyword: )?class (\d+)\s+([0-9.]+)", text)
+        assert len(rows) == 5, text
+        kth = np.sort(ref)[-5]
+        for cls, score in rows:
+            assert abs(ref[int(cls)] - float(score)) <= 1.5e-3, (cls, score, ref[int(cls)])
+            assert ref[int(cls)] >= kth - 2e-3, (cls, ref[int(cls)], kth)
 
 
 def test_empty_and_single_clip_batches():

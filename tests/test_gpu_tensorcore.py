@@ -5,8 +5,8 @@ Stated tolerance (north_star: "logits within a stated bf16 tolerance with identi
 fp32 accumulate / residual / LayerNorm / softmax.  ONE bound per weight set, in logits and in probabilities:
   'init'    (reference-like init statistics, flat 0.3-0.7 outputs):  |d logit| <= 5e-3, |d prob| <= 1e-3; top-5 compared
             tie-aware (literal top-5 equality is unattainable on flat outputs even in TF32: SURVEY 7.2);
-  'trained' (large-magnitude blocks + sparse-activation head, helpers.make_state_dict): |d logit| <= EPS_LOGIT['trained'],
-            |d prob| <= TOL['trained']; LITERAL top-5 set equality on every clip whose reference 5th / 6th logits are more
+  'trained' (large-magnitude blocks + sparse-activation head, helpers.make_state_dict): |d logit| <= 0.08 (measured 0.057 on
+            UiT-XS, 0.030 XXS, 0.029 XXXS), |d prob| <= 1.5e-2 (measured 8.5e-3); LITERAL top-5 set equality on every clip whose reference 5th / 6th logits are more
             than 2*eps apart, with the assertion that the strict `must` set is non-empty on >= 90 % of the clips (the check
             cannot go vacuous)."""
 import numpy as np
@@ -18,8 +18,9 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL = {"init": 1e-3, "trained": 2.5e-2}
-EPS_LOGIT = {"init": 5e-3, "trained": 0.1}
+# measured on B200 (round 2): init 1.9e-3 logit / 4.7e-4 prob; trained 5.7e-2 logit (XS, 12 blocks; the worst clip is a 2400-sample one) / 8.6e-3 prob
+TOL = {"init": 1e-3, "trained": 1.5e-2}
+EPS_LOGIT = {"init": 5e-3, "trained": 0.08}
 
 
 def pack_kmajor(w: torch.Tensor) -> torch.Tensor:
@@ -87,11 +88,13 @@ def test_bf16_residual_stream_vs_reference_trace(depth):
     x = torch.from_numpy(H.noise_clips(32)[:2]).to(DEV)
     N_.lib().uitk_debug_taps(1)
     try:
-        m(x)
+        db, mp = m.front_end.logmel_unclamped(x)
+        ws = []
+        m.encode(db, mp, workspace_out=ws)
         torch.cuda.synchronize()
     finally:
         N_.lib().uitk_debug_taps(0)
-    tok = m._last_workspace[: 2 * 24 * 128 * 4].view(torch.float32).view(2, 24, 128).cpu().numpy()
+    tok = ws[0][: 2 * 24 * 128 * 4].view(torch.float32).view(2, 24, 128).cpu().numpy()
     ref = z["blocks"][depth - 1]
     err = np.abs(tok - ref).max()
     print(f"depth {depth}: max|d| {err:.4f}  ref max {np.abs(ref).max():.2f}")
@@ -135,7 +138,7 @@ def test_bf16_scores_vs_reference_golden(arch, kind):
     if kind == "trained":
         assert rep["decisive_match_frac"] == 1.0, rep          # literal top-5 wherever the reference is decisive
         must_nonempty = np.mean([(H.logits_of(r) > np.sort(H.logits_of(r))[-5] + 2 * EPS_LOGIT[kind]).any() for r in ref])
-        assert must_nonempty >= 0.9 and rep["decisive_frac"] >= 0.4, (must_nonempty, rep)   # never vacuous
+        assert must_nonempty >= 0.9 and rep["decisive_frac"] >= 0.5, (must_nonempty, rep)   # never vacuous
     else:
         assert H.tie_aware_topk_equal(ref, got, 5, eps=TOL[kind])
 

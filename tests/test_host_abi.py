@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.uitk_version() == 103
+    assert lib.uitk_version() == 200
 
 
 def test_geometry_helpers_match_oracle(lib):
@@ -71,14 +71,22 @@ def test_encoder_pack_tensor_order_and_size(lib):
     from uit_mobile_b200 import _native as N
     names = N.encoder_tensor_names(4)
     sd = H.make_state_dict("uit_xxxs")
-    assert len(names) == 14 + 12 * 4 and all(n in sd for n in names)
+    assert len(names) == 16 + 12 * 4 and all(n in sd for n in names)
     dead = set(sd) - set(names)
-    assert dead == {"cls_token", "token_pos_embed", "front_end.0.spectrogram.window", "front_end.0.mel_scale.fb",
-                    "init_bn.1.num_batches_tracked"}
+    assert dead == {"front_end.0.spectrogram.window", "front_end.0.mel_scale.fb", "init_bn.1.num_batches_tracked"}
     cfg = N.EncoderCfg(4, 537, 6, 0)
     assert lib.uitk_encoder_blob_bytes(C.byref(cfg)) > 4 * 568089 * 0.9
     bad = N.EncoderCfg(4, 5000, 6, 0)
     assert lib.uitk_encoder_blob_bytes(C.byref(bad)) == 0 and b"outputdim" in lib.uitk_last_error()
+    bad = N.EncoderCfg(4, 537, 6, 0, attention=2)
+    assert lib.uitk_encoder_blob_bytes(C.byref(bad)) == 0 and b"attention" in lib.uitk_last_error()
+    # variants: the full Attention blob is larger (qkv 384 x 128, proj 128 x 128); only the UiT configuration carries a bf16 section
+    full = N.EncoderCfg(4, 537, 6, 1, attention=1)
+    assert lib.uitk_encoder_blob_bytes(C.byref(full)) > lib.uitk_encoder_blob_bytes(C.byref(cfg)) + 4 * 4 * (288 * 128 + 96 * 128)
+    assert N.EncoderCfg(4, 537, 6, 1).tensor_core and not full.tensor_core and not N.EncoderCfg(4, 537, 6, 1, pooling=1).tensor_core
+    for pooling, extra in ((0, 0), (1, 1), (2, 0)):
+        c = N.EncoderCfg(4, 537, 6, 0, pooling=pooling)
+        assert lib.uitk_tokens_total(C.byref(c), 101, 102) == 24 + extra and lib.uitk_tokens_total(C.byref(c), 90, 102) == 20 + extra
 
 
 def _bf16_to_f32(u16: np.ndarray) -> np.ndarray:
@@ -181,13 +189,32 @@ def test_module_contract():
 def test_tile_clips_and_fused_stage_methods(lib):
     import uit_mobile_b200 as U
     m = U.models.uit_xxxs(outputdim=537, target_length=102)
-    assert m.tile_clips(101) == 5            # 1 s clip: 24 tokens -> 5 clips per 128-row tile
-    assert m.tile_clips(1001) == 1           # 10 s clip: 10 crops of 24 tokens -> tiles already cut at clip boundaries? (gcd rule)
-    assert m.tile_clips(16) == 32            # 2400 samples: 4 tokens
-    with pytest.raises(NotImplementedError):
+    from uit_mobile_b200 import _native as N
+    assert m.tile_clips(101) == 5            # 1 s clip: 24 token slots -> 5 clips per 128-row tile
+    assert m.tile_clips(1001) == 1           # 10 s clip: 10 crops -> a clip's crops fill whole tiles
+    assert m.tile_clips(16) == 5             # 2400 samples: still 24 slots per clip (4 live), 5 clips per tile
+    m.eval()
+    with pytest.raises(N.UitkError):         # forward_features / forward_head are real entry points now: CUDA only, no fallback
         m.forward_features(torch.zeros(1, 1, 64, 102))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(N.UitkError):
         m.forward_head(torch.zeros(1, 24, 128))
+    with pytest.raises(N.UitkError):
+        m.init_bn(torch.zeros(1, 1, 64, 102))
+
+
+def test_variant_factories_keep_the_reference_state_dict():
+    """full Attention / GELU / pooling 'token' | 'dm' behind the same factories; shapes as the reference builds them
+    (tests/golden/generate_golden.py loads the same state_dicts into the reference with strict=True)."""
+    import uit_mobile_b200 as U
+    for name, (depth, attention, act, pooling) in H.VARIANTS.items():
+        m = H.build_variant(U.models, name)
+        sd = H.make_state_dict(name)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(v.shape)) for k, v in sd.items()], name
+        m.load_state_dict(sd, strict=True)
+        assert m.pooling == pooling and m.attention_type == attention and len(m.blocks) == depth
+        assert isinstance(m.blocks[0].mlp.act, torch.nn.ReLU if act == "relu" else torch.nn.GELU)
+        assert not m._cfg().tensor_core
+    assert U.models.uit_xs(target_length=102)._cfg().tensor_core and not U.models.uit_xs(target_length=102, precision="fp32")._cfg().tensor_core
 
 
 def test_pos_embed_resize_on_load():
@@ -207,8 +234,10 @@ def test_unsupported_configurations_raise():
     import uit_mobile_b200 as U
     with pytest.raises(NotImplementedError):
         U.models.UITBase()                                            # reference defaults: 768-dim token-pooled ViT
+    with pytest.raises(KeyError):
+        U.models.audio_transformer_h128_d3_m3_bneck_v2_relu()         # names an attention class the reference never defines (Q10)
     with pytest.raises(NotImplementedError):
-        U.models.uit_xs(pooling="token")
+        U.models.uit_xs(embed_dim=192)
     with pytest.raises(NotImplementedError):
         U.models.uit_xs(n_mels=80)
     with pytest.raises(NotImplementedError):

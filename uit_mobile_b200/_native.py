@@ -20,8 +20,23 @@ class UitkError(RuntimeError):
     pass
 
 
+ATTENTION = {"BNeckAttention": 0, "Attention": 1}
+ACT = {"relu": 0, "gelu": 1}
+POOLING = {"mean": 0, "token": 1, "dm": 2}
+
+
 class EncoderCfg(C.Structure):
-    _fields_ = [("depth", C.c_int), ("outputdim", C.c_int), ("grid_t", C.c_int), ("precision", C.c_int)]
+    """uitk_encoder_cfg (include/uitk.h)."""
+    _fields_ = [("depth", C.c_int), ("outputdim", C.c_int), ("grid_t", C.c_int), ("precision", C.c_int),
+                ("attention", C.c_int), ("act", C.c_int), ("pooling", C.c_int), ("reserved", C.c_int)]
+
+    def __init__(self, depth=0, outputdim=0, grid_t=0, precision=0, attention=0, act=0, pooling=0):
+        super().__init__(depth, outputdim, grid_t, precision, attention, act, pooling, 0)
+
+    @property
+    def tensor_core(self) -> bool:
+        """The configuration the tcgen05 megakernel implements (UiT-XS/XXS/XXXS); everything else runs the fp32 kernels."""
+        return self.precision == PREC_BF16 and self.attention == 0 and self.act == 0 and self.pooling == 0
 
 
 # name -> (restype, argtypes); every symbol declared in include/uitk.h
@@ -32,6 +47,7 @@ SIGNATURES = {
     "uitk_num_frames": (C.c_int64, [C.c_int64]),
     "uitk_num_crops": (C.c_int, [C.c_int64, C.c_int]),
     "uitk_tokens_per_crop": (C.c_int, [C.c_int64, C.c_int]),
+    "uitk_tokens_total": (C.c_int, [C.POINTER(EncoderCfg), C.c_int64, C.c_int]),
     "uitk_frontend_blob_bytes": (C.c_size_t, [C.c_void_p]),
     "uitk_pack_frontend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "uitk_logmel": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -47,6 +63,13 @@ SIGNATURES = {
     "uitk_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
     "uitk_encoder": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uitk_encoder_fixup": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uitk_init_bn": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "uitk_forward_features_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64]),
+    "uitk_forward_features": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
+    "uitk_forward_head": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "uitk_encoder_tokens_offset": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
     "uitk_debug_taps": (None, [C.c_int]),
     "uitk_debug_read_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -69,6 +69,10 @@ int uitk_logmel_sliding(const float* d_stream, int64_t n_samples, int64_t window
   UITK_REQUIRE(window >= 4 * UITK_HOP && window % UITK_HOP == 0 && window <= (1ll << 30), UITK_EINVAL,
                "window %lld must be a multiple of 160 samples, at least 640", (long long)window);
   UITK_REQUIRE(n_samples >= window && n_samples <= (1ll << 30), UITK_EINVAL, "stream shorter than one window (or longer than 2^30 samples)");
+  // every stream frame computed below must be an interior frame of SOME window, or it would leak into the batch max / min
+  UITK_REQUIRE(hop / UITK_HOP <= window / UITK_HOP - 3, UITK_EINVAL,
+               "window hop %lld leaves stream frames that belong to no window (need hop <= window - 480); use uitk_logmel with ld_wav = hop",
+               (long long)hop);
   UITK_REQUIRE(aligned(d_stream, 4) && aligned(d_db, 4) && aligned(d_max_pow, 4) && aligned(d_frontend_blob, 16) && aligned(d_workspace, 4),
                UITK_EALIGN, "misaligned pointer");
   UITK_REQUIRE(workspace_bytes >= uitk_logmel_sliding_workspace_bytes(n_samples), UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
@@ -108,16 +112,16 @@ static int encoder_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, i
   UITK_REQUIRE(target_length >= 16 && target_length <= 16 * cfg->grid_t + 15, UITK_EINVAL,
                "target_length %d incompatible with time_pos_embed length %d", target_length, cfg->grid_t);
   UITK_REQUIRE(T >= 16, UITK_EINVAL, "need at least 16 frames (2400 samples) for one patch, got %lld", (long long)T);
-  *rows = B * crops_for(T, target_length) * 4 * time_patches_for(T, target_length);
+  *rows = B * crops_for(T, target_length) * tokens_total_for(*cfg, T, target_length);
   return UITK_OK;
 }
 
 size_t uitk_encoder_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
   int64_t rows = 0;
   if (encoder_geometry(cfg, B, T, target_length, &rows) != UITK_OK) return 0;
-  if (cfg->precision == UITK_PREC_BF16 && time_patches_for(T, target_length) == 6)       // 24 tokens: tensor-core megakernel
-    return encoder_tc_workspace_bytes(B * crops_for(T, target_length), rows) + 256;
-  return encoder_fp32_workspace_bytes(rows) + 256;
+  const int64_t RR = B * crops_for(T, target_length);
+  if (tc_config(*cfg)) return encoder_tc_workspace_bytes(RR, RR * 24) + 256;       // tensor-core megakernel: 24 row slots per clip-crop
+  return encoder_fp32_workspace_bytes(*cfg, RR * tokens_total_for(*cfg, T, target_length)) + 256;
 }
 
 size_t uitk_encoder_tokens_offset(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length) {
@@ -140,10 +144,84 @@ int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const 
   if (rc != UITK_OK) return rc;
   EncoderArgs a{cfg, d_encoder_blob, d_db, B, T, target_length, eval_avg, d_max_pow, d_probs,
                 d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), g_debug_taps};
-  if (cfg->precision == UITK_PREC_FP32) return run_encoder_fp32(a);
-  if (cfg->precision == UITK_PREC_BF16) return run_encoder_tc(a);
-  set_error("unknown precision %d", cfg->precision);
-  return UITK_EINVAL;
+  UITK_REQUIRE(cfg->precision == UITK_PREC_FP32 || cfg->precision == UITK_PREC_BF16, UITK_EINVAL, "unknown precision %d", cfg->precision);
+  return tc_config(*cfg) ? run_encoder_tc(a) : run_encoder_fp32(a);
+}
+
+int uitk_encoder_fixup(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
+                       int target_length, int eval_avg, const uint32_t* d_max_pow, const uint32_t* d_max_used,
+                       const uint32_t* d_min_pow, float* d_probs, void* d_workspace, size_t workspace_bytes, void* stream) {
+  UITK_REQUIRE(cfg && d_encoder_blob && d_db && d_max_pow && d_max_used && d_min_pow && d_probs && d_workspace, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(eval_avg == 0 || eval_avg == 1, UITK_EINVAL, "eval_avg must be 0 (mean) or 1 (max)");
+  UITK_REQUIRE(tc_config(*cfg), UITK_EINVAL, "uitk_encoder_fixup needs the tensor-core configuration (bf16, BNeckAttention, ReLU, mean pooling)");
+  UITK_REQUIRE(aligned(d_workspace, 256) && aligned(d_encoder_blob, 256) && aligned(d_db, 4) && aligned(d_probs, 4), UITK_EALIGN,
+               "misaligned pointer (workspace and blob need 256-byte alignment)");
+  int64_t rows = 0;
+  int rc = encoder_geometry(cfg, B, T, target_length, &rows);
+  if (rc != UITK_OK) return rc;
+  if (B == 0) return UITK_OK;
+  rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  EncoderArgs a{cfg, d_encoder_blob, d_db, B, T, target_length, eval_avg, d_max_pow, d_probs,
+                d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), 0};
+  a.cond_used = d_max_used; a.cond_min = d_min_pow;
+  return run_encoder_tc(a);
+}
+
+static int features_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T) {
+  UITK_REQUIRE(cfg, UITK_EINVAL, "null cfg");
+  UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
+  UITK_REQUIRE(T >= 16 && T <= 16 * cfg->grid_t + 15, UITK_EINVAL,
+               "forward_features takes 16..%d frames (time_pos_embed has %d entries), got %lld", 16 * cfg->grid_t + 15, cfg->grid_t, (long long)T);
+  return UITK_OK;
+}
+
+size_t uitk_forward_features_workspace_bytes(const uitk_encoder_cfg* cfg, int64_t B, int64_t T) {
+  if (features_geometry(cfg, B, T) != UITK_OK) return 0;
+  const int target = 16 * cfg->grid_t + 15;
+  if (tc_config(*cfg)) return encoder_tc_workspace_bytes(B, B * 24) + 256;
+  return encoder_fp32_workspace_bytes(*cfg, B * tokens_total_for(*cfg, T, target)) + 256;
+}
+
+int uitk_forward_features(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_spec, int64_t B, int64_t T,
+                          float* d_tokens, void* d_workspace, size_t workspace_bytes, void* stream) {
+  UITK_REQUIRE(cfg && d_encoder_blob && d_spec && d_tokens && d_workspace, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(aligned(d_workspace, 256) && aligned(d_encoder_blob, 256) && aligned(d_spec, 4) && aligned(d_tokens, 16), UITK_EALIGN,
+               "misaligned pointer (workspace and blob need 256-byte alignment, tokens 16)");
+  int rc = features_geometry(cfg, B, T);
+  if (rc != UITK_OK) return rc;
+  if (B == 0) return UITK_OK;
+  rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  static const uint32_t* no_word = nullptr;
+  EncoderArgs a{cfg, d_encoder_blob, d_spec, B, T, 16 * cfg->grid_t + 15, 0, no_word, nullptr,
+                d_workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), 0};
+  a.features_out = d_tokens;
+  return tc_config(*cfg) ? run_encoder_tc(a) : run_encoder_fp32(a);
+}
+
+int uitk_forward_head(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_tokens, int64_t B, int n_tokens,
+                      float* d_probs, void* stream) {
+  UITK_REQUIRE(cfg && d_encoder_blob && d_tokens && d_probs, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(B >= 0, UITK_EINVAL, "negative batch");
+  UITK_REQUIRE(n_tokens >= 1 && n_tokens <= UITK_MAX_TOKENS + 1, UITK_EINVAL, "n_tokens %d outside [1, %d]", n_tokens, UITK_MAX_TOKENS + 1);
+  UITK_REQUIRE(cfg->pooling != UITK_POOL_DM || n_tokens % 4 == 0, UITK_EINVAL, "pooling='dm' needs 4 * t tokens, got %d", n_tokens);
+  UITK_REQUIRE(aligned(d_tokens, 16) && aligned(d_encoder_blob, 256) && aligned(d_probs, 4), UITK_EALIGN, "misaligned pointer");
+  if (B == 0) return UITK_OK;
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return run_forward_head(*cfg, d_encoder_blob, d_tokens, B, n_tokens, d_probs, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int uitk_init_bn(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T, float* d_out,
+                 void* stream) {
+  UITK_REQUIRE(cfg && d_encoder_blob && d_db && d_out, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(B >= 0 && T >= 1, UITK_EINVAL, "bad shape");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  const EncoderLayout lay = make_encoder_layout(*cfg);
+  const float* W = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(d_encoder_blob) + sizeof(BlobHeader));
+  return launch_init_bn(d_db, B, T, W + lay.bn_scale, W + lay.bn_shift, d_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 void uitk_debug_taps(int enable) { g_debug_taps = enable; }

@@ -5,6 +5,9 @@
 //   patch GEMM  = top-dB clamp + eval BatchNorm (460-462) + Conv2d 16x16/16 as [rows,256]x[256,128] + pos (380-388)
 //   per block   = LN1+qkv GEMM | attention (89-122) | proj GEMM + residual | LN2+fc1 GEMM+ReLU | fc2 GEMM + residual
 //   head        = final LN(1e-6), token mean, LN(1e-5), Linear 128->outputdim, sigmoid, crop mean/max (395-404, 468-488)
+// It is also the implementation of the UITBase variants the tensor-core megakernel does not cover: full
+// Attention (2 heads x 64, uit.py:124-178), GELU MLP (uit.py:338), pooling='token' (cls row, uit.py:389-392, 399-401) and
+// pooling='dm' (uit.py:405-412), and of uitk_forward_features / uitk_forward_head (uit.py:379-412).
 #include "uitk_common.cuh"
 
 namespace uitk {
@@ -12,7 +15,7 @@ namespace uitk {
 namespace {
 
 enum { PRO_PLAIN = 0, PRO_LN = 1, PRO_PATCH = 2 };
-enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESID = 2, EPI_PATCH = 3, EPI_SIGMOID = 4 };
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESID = 2, EPI_PATCH = 3, EPI_SIGMOID = 4, EPI_BIAS_GELU = 5 };
 
 struct GemmParams {
   const float* A; int lda;
@@ -27,6 +30,9 @@ struct GemmParams {
   const float* db; int T; int crops; int tokens; int t_n; int target;
   const float* bn_scale; const float* bn_shift; const uint32_t* max_pow;
   const float* time_pos; const float* freq_pos;
+  int no_clamp;    // PRO_PATCH: the input is an already normalised spectrogram (uitk_forward_features)
+  int out_tt;      // EPI_PATCH: rows per crop in C (tokens, +1 when a cls row leads every crop) ...
+  int out_off;     // ... and the row offset of the first patch token inside a crop (1 with a cls row)
 };
 
 constexpr int BM = 128, KS = 32, AS_LD = 36;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
     }
   }
   float cutoff = 0.f;
-  if (PRO == PRO_PATCH) cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+  if (PRO == PRO_PATCH) cutoff = p.no_clamp ? -INFINITY : 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
 
   float acc[8][TN];
 #pragma unroll
@@ -142,9 +148,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
     const int row = row0 + ty * 8 + i;
     if (row >= p.M) continue;
     int f = 0, tau = 0;
+    size_t crow = row;
     if (EPI == EPI_PATCH) {
       const int rr = row / p.tokens, tok = row - rr * p.tokens;
       f = tok / p.t_n; tau = tok - f * p.t_n;
+      crow = (size_t)rr * p.out_tt + p.out_off + tok;
     }
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
@@ -155,43 +163,45 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams p) {
         continue;
       }
       if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      if (EPI == EPI_BIAS_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));   // nn.GELU() (exact erf)
       if (EPI == EPI_PATCH) { v += p.time_pos[tau * 128 + col]; v += p.freq_pos[f * 128 + col]; }
-      float* dst = p.C + (size_t)row * p.ldc + col;
+      float* dst = p.C + crow * p.ldc + col;
       if (EPI == EPI_BIAS_RESID) v = *dst + v;
       *dst = v;
     }
   }
 }
 
-// One warp per (clip-crop, head); lane i < tokens owns query row i.  qkv rows are [q(2x16) | k(2x16) | v(2x16)].
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ o,
-                                                        int RR, int tokens, float scale) {
-  __shared__ float s[4][UITK_MAX_TOKENS * 96];
+// One warp per (clip-crop, head); lane i < tokens owns query row i.  qkv rows are [q(2 x HD) | k(2 x HD) | v(2 x HD)];
+// HD = 16 (BNeckAttention) or 64 (Attention); tokens <= 25.  CLIPS clip-crops per CTA (shared-memory budget).
+template <int HD, int CLIPS>
+__global__ void __launch_bounds__(CLIPS * 64) attention_kernel(const float* __restrict__ qkv, float* __restrict__ o,
+                                                               int RR, int tokens, float scale) {
+  constexpr int kMaxTok = UITK_MAX_TOKENS + 1, ROW = 6 * HD;
+  __shared__ float s[CLIPS][kMaxTok * ROW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rr0 = blockIdx.x * 4;
-  for (int lr = 0; lr < 4; ++lr) {
+  const int rr0 = blockIdx.x * CLIPS;
+  for (int lr = 0; lr < CLIPS; ++lr) {
     const int rr = rr0 + lr;
     if (rr >= RR) break;
-    const float* src = qkv + (size_t)rr * tokens * 96;
-    for (int i = tid; i < tokens * 96; i += 256) s[lr][i] = src[i];
+    const float* src = qkv + (size_t)rr * tokens * ROW;
+    for (int i = tid; i < tokens * ROW; i += CLIPS * 64) s[lr][i] = src[i];
   }
   __syncthreads();
   const int lr = warp >> 1, head = warp & 1;
   const int rr = rr0 + lr;
   if (rr >= RR || lane >= tokens) return;
   const float* base = s[lr];
-  float q[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) q[d] = base[lane * 96 + head * 16 + d];
-  float sc[UITK_MAX_TOKENS];
+  const float* qi = base + lane * ROW + head * HD;
+  float sc[kMaxTok];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+  for (int j = 0; j < kMaxTok; ++j) {
     float a = 0.f;
     if (j < tokens) {
-      const float* kj = base + j * 96 + 32 + head * 16;
+      const float* kj = base + j * ROW + 2 * HD + head * HD;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) a = fmaf(q[d], kj[d], a);
+      for (int d = 0; d < HD; ++d) a = fmaf(qi[d], kj[d], a);
       a *= scale;
       mx = fmaxf(mx, a);
     }
@@ -199,32 +209,80 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
+  for (int j = 0; j < kMaxTok; ++j) {
     sc[j] = j < tokens ? expf(sc[j] - mx) : 0.f;
     sum += sc[j];
   }
   const float inv = 1.f / sum;
-  float out[16];
+  float* dst = o + ((size_t)rr * tokens + lane) * (2 * HD) + head * HD;
+#pragma unroll 1
+  for (int d0 = 0; d0 < HD; d0 += 16) {
+    float out[16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) out[d] = 0.f;
+    for (int d = 0; d < 16; ++d) out[d] = 0.f;
 #pragma unroll
-  for (int j = 0; j < UITK_MAX_TOKENS; ++j) {
-    if (j < tokens) {
-      const float pj = sc[j] * inv;
-      const float* vj = base + j * 96 + 64 + head * 16;
+    for (int j = 0; j < kMaxTok; ++j) {
+      if (j < tokens) {
+        const float pj = sc[j] * inv;
+        const float* vj = base + j * ROW + 4 * HD + head * HD + d0;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) out[d] = fmaf(pj, vj[d], out[d]);
+        for (int d = 0; d < 16; ++d) out[d] = fmaf(pj, vj[d], out[d]);
+      }
     }
-  }
-  float* dst = o + ((size_t)rr * tokens + lane) * 32 + head * 16;
 #pragma unroll
-  for (int d = 0; d < 16; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(out[d], out[d + 1], out[d + 2], out[d + 3]);
+    for (int d = 0; d < 16; d += 4) *reinterpret_cast<float4*>(dst + d0 + d) = make_float4(out[d], out[d + 1], out[d + 2], out[d + 3]);
+  }
 }
 
-// One CTA per clip: final LN per token, token mean, head LN, Linear + sigmoid, reduce over crops.
-// POOLED: x already holds the token-mean of the final-LayerNorm output, [B*crops][128] (tensor-core path).
-template <bool POOLED>
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int crops, int tokens,
+// cls rows of pooling='token': x[rr * tt + 0][:] = cls_token + token_pos_embed (uit.py:389-392)
+__global__ void cls_fill_kernel(float* __restrict__ x, int RR, int tt, const float* __restrict__ cls_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < RR * 128) x[(size_t)(i >> 7) * tt * 128 + (i & 127)] = cls_row[i & 127];
+}
+
+// Final LayerNorm (eps 1e-6, affine) of token rows, one warp per output row: out[rr][j] = LN(x[rr * slots + map(j)]),
+// map(j) = (j / t_n) * slot_tn + j % t_n  (identity when slot_tn == t_n; the tensor-core tile keeps 6 time slots per mel band).
+__global__ void __launch_bounds__(256) final_ln_kernel(const float* __restrict__ x, long long rows_out, int n_out, int slots, int t_n,
+                                                       int slot_tn, const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows_out) return;
+  const long long rr = row / n_out;
+  const int j = (int)(row - rr * n_out);
+  const int src = slot_tn == t_n ? j : (j / t_n) * slot_tn + j % t_n;
+  const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)rr * slots + src) * 128 + lane * 4);
+  float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / 128.f);
+  const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+  float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-6f);
+  const float4 g = *reinterpret_cast<const float4*>(w + lane * 4), be = *reinterpret_cast<const float4*>(b + lane * 4);
+  *reinterpret_cast<float4*>(out + (size_t)row * 128 + lane * 4) =
+      make_float4(d0 * rstd * g.x + be.x, d1 * rstd * g.y + be.y, d2 * rstd * g.z + be.z, d3 * rstd * g.w + be.w);
+}
+
+// eval-mode init_bn on a [B, 64, T] log-mel (uit.py:310-313, 460-462): out = x * scale[mel] + shift[mel]
+__global__ void init_bn_kernel(const float* __restrict__ db, long long n, int T, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int mel = (int)((i / T) & 63);
+    out[i] = fmaf(db[i], scale[mel], shift[mel]);
+  }
+}
+
+// One CTA per clip: [final LN per token,] pooling, head LN, Linear + sigmoid, reduce over crops.
+//   APPLY_NORM: x holds the residual stream and the final LayerNorm (eps 1e-6) is applied here; otherwise x already holds
+//               forward_features' output (uitk_forward_head).
+//   pooling (uit.py:398-412): MEAN  - one group of all tokens;  TOKEN - one group = row 0 (the cls token);
+//               DM - t_n groups {f * t_n + tau | f < 4}: frequency mean per time step, head + sigmoid per step, mean of the scores.
+template <bool APPLY_NORM>
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int crops, int tokens, int pooling, int t_n,
                                                    const float* __restrict__ norm_w, const float* __restrict__ norm_b,
                                                    const float* __restrict__ hln_w, const float* __restrict__ hln_b,
                                                    const float* __restrict__ head_wt, const float* __restrict__ head_b,
@@ -235,69 +293,84 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
   const size_t b = blockIdx.x;
   float accp[3] = {0.f, 0.f, 0.f};
   if (eval_max) accp[0] = accp[1] = accp[2] = -INFINITY;
+  const int n_groups = pooling == UITK_POOL_DM ? t_n : 1;
+  const float4 g = *reinterpret_cast<const float4*>(norm_w + lane * 4);
+  const float4 be = *reinterpret_cast<const float4*>(norm_b + lane * 4);
   for (int c = 0; c < crops; ++c) {
-    const float* xc = x + (b * crops + c) * (size_t)(POOLED ? 1 : tokens) * 128;
-    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (POOLED && warp == 0) ps = *reinterpret_cast<const float4*>(xc + lane * 4);
-    const float4 g = *reinterpret_cast<const float4*>(norm_w + lane * 4);
-    const float4 be = *reinterpret_cast<const float4*>(norm_b + lane * 4);
-    for (int t = warp; t < (POOLED ? 0 : tokens); t += 8) {
-      const float4 v = *reinterpret_cast<const float4*>(xc + (size_t)t * 128 + lane * 4);
-      float s = v.x + v.y + v.z + v.w;
+    const float* xc = x + (b * crops + c) * (size_t)tokens * 128;
+    float crop_p[3] = {0.f, 0.f, 0.f};
+    for (int grp = 0; grp < n_groups; ++grp) {
+      // rows of this group: first, step, count
+      int first = 0, step = 1, count = tokens;
+      if (pooling == UITK_POOL_TOKEN) count = 1;
+      if (pooling == UITK_POOL_DM) { first = grp; step = t_n; count = 4; }
+      float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = warp; i < count; i += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(xc + (size_t)(first + i * step) * 128 + lane * 4);
+        if (APPLY_NORM) {
+          float s = v.x + v.y + v.z + v.w;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s * (1.f / 128.f);
-      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mean = s * (1.f / 128.f);
+          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+          float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-6f);
-      ps.x += d0 * rstd * g.x + be.x; ps.y += d1 * rstd * g.y + be.y;
-      ps.z += d2 * rstd * g.z + be.z; ps.w += d3 * rstd * g.w + be.w;
-    }
-    __syncthreads();   // previous crop's readers of pooled/part are done
-    *reinterpret_cast<float4*>(&part[warp][lane * 4]) = ps;
-    __syncthreads();
-    if (warp == 0) {
-      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float4 t4 = *reinterpret_cast<const float4*>(&part[w][lane * 4]);
-        m.x += t4.x; m.y += t4.y; m.z += t4.z; m.w += t4.w;
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-6f);
+          ps.x += d0 * rstd * g.x + be.x; ps.y += d1 * rstd * g.y + be.y;
+          ps.z += d2 * rstd * g.z + be.z; ps.w += d3 * rstd * g.w + be.w;
+        } else {
+          ps.x += v.x; ps.y += v.y; ps.z += v.z; ps.w += v.w;
+        }
       }
-      const float invn = POOLED ? 1.f : 1.f / (float)tokens;
-      m.x *= invn; m.y *= invn; m.z *= invn; m.w *= invn;
-      float s = m.x + m.y + m.z + m.w;
+      __syncthreads();   // previous group's readers of pooled/part are done
+      *reinterpret_cast<float4*>(&part[warp][lane * 4]) = ps;
+      __syncthreads();
+      if (warp == 0) {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s * (1.f / 128.f);
-      const float d0 = m.x - mean, d1 = m.y - mean, d2 = m.z - mean, d3 = m.w - mean;
-      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        for (int w = 0; w < 8; ++w) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&part[w][lane * 4]);
+          m.x += t4.x; m.y += t4.y; m.z += t4.z; m.w += t4.w;
+        }
+        const float invn = 1.f / (float)count;
+        m.x *= invn; m.y *= invn; m.z *= invn; m.w *= invn;
+        float s = m.x + m.y + m.z + m.w;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
-      const float4 hg = *reinterpret_cast<const float4*>(hln_w + lane * 4);
-      const float4 hb = *reinterpret_cast<const float4*>(hln_b + lane * 4);
-      *reinterpret_cast<float4*>(&pooled[lane * 4]) =
-          make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.f / 128.f);
+        const float d0 = m.x - mean, d1 = m.y - mean, d2 = m.z - mean, d3 = m.w - mean;
+        float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
+        const float4 hg = *reinterpret_cast<const float4*>(hln_w + lane * 4);
+        const float4 hb = *reinterpret_cast<const float4*>(hln_b + lane * 4);
+        *reinterpret_cast<float4*>(&pooled[lane * 4]) =
+            make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int oidx = tid + 256 * r;
+        if (oidx < outputdim) {
+          float z = head_b[oidx];
+#pragma unroll 8
+          for (int k = 0; k < 128; ++k) z = fmaf(pooled[k], __ldg(head_wt + (size_t)k * ld_head + oidx), z);
+          crop_p[r] += 1.f / (1.f + expf(-z));
+        }
+      }
     }
-    __syncthreads();
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int oidx = tid + 256 * r;
-      if (oidx < outputdim) {
-        float z = head_b[oidx];
-#pragma unroll 8
-        for (int k = 0; k < 128; ++k) z = fmaf(pooled[k], __ldg(head_wt + (size_t)k * ld_head + oidx), z);
-        const float pr = 1.f / (1.f + expf(-z));
-        accp[r] = eval_max ? fmaxf(accp[r], pr) : accp[r] + pr;
-      }
+      const float pr = n_groups == 1 ? crop_p[r] : crop_p[r] / (float)n_groups;
+      accp[r] = eval_max ? fmaxf(accp[r], pr) : accp[r] + pr;
     }
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int oidx = tid + 256 * r;
-    if (oidx < outputdim) probs[b * outputdim + oidx] = eval_max ? accp[r] : accp[r] / (float)crops;
+    if (oidx < outputdim) probs[b * outputdim + oidx] = eval_max ? accp[r] : (crops == 1 ? accp[r] : accp[r] / (float)crops);
   }
 }
 
@@ -305,72 +378,129 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-size_t encoder_fp32_workspace_bytes(int64_t rows) {
+size_t encoder_fp32_workspace_bytes(const uitk_encoder_cfg& cfg, int64_t rows) {
   const size_t r = (size_t)rows;
-  return align_up(r * 128 * 4, 256) + align_up(r * 96 * 4, 256) + align_up(r * 32 * 4, 256) + align_up(r * 384 * 4, 256);
+  const size_t qkv_n = cfg.attention == UITK_ATTN_FULL ? 384 : 96, inner = cfg.attention == UITK_ATTN_FULL ? 128 : 32;
+  return align_up(r * 128 * 4, 256) + align_up(r * qkv_n * 4, 256) + align_up(r * inner * 4, 256) + align_up(r * 384 * 4, 256);
+}
+
+int launch_final_ln(const float* x, int64_t RR, int slots, int t_n, int slot_tn, const float* norm_w, const float* norm_b, float* out,
+                    cudaStream_t s) {
+  // n_out rows per crop: the compact token count (cls row included when slots is the compact count + 1)
+  const int n_out = slot_tn == t_n ? slots : 4 * t_n;
+  const long long rows = (long long)RR * n_out;
+  if (rows == 0) return UITK_OK;
+  final_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, rows, n_out, slots, t_n, slot_tn, norm_w, norm_b, out);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+int launch_init_bn(const float* db, int64_t B, int64_t T, const float* scale, const float* shift, float* out, cudaStream_t s) {
+  const long long n = (long long)B * 64 * T;
+  if (n == 0) return UITK_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  init_bn_kernel<<<(int)blocks, 256, 0, s>>>(db, n, (int)T, scale, shift, out);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
+}
+
+int run_forward_head(const uitk_encoder_cfg& cfg, const void* blob, const float* tokens, int64_t B, int n_tokens, float* probs,
+                     cudaStream_t s) {
+  const EncoderLayout lay = make_encoder_layout(cfg);
+  const float* W = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(blob) + sizeof(BlobHeader));
+  const int t_n = cfg.pooling == UITK_POOL_DM ? n_tokens / 4 : 0;
+  head_kernel<false><<<(unsigned)B, 256, 0, s>>>(tokens, 1, n_tokens, cfg.pooling, t_n, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w,
+                                                 W + lay.hln_b, W + lay.head_wt, W + lay.head_b, cfg.outputdim, lay.outputdim_padded, 0, probs);
+  count_launches(1);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  return UITK_OK;
 }
 
 int run_encoder_fp32(const EncoderArgs& a) {
   const uitk_encoder_cfg& cfg = *a.cfg;
-  const int crops = crops_for(a.T, a.target_length);
+  const bool feat = a.features_out != nullptr;
+  const int crops = feat ? 1 : crops_for(a.T, a.target_length);
   const int t_n = time_patches_for(a.T, a.target_length);
-  const int tokens = 4 * t_n;
+  const int tokens = 4 * t_n;                                          // patch tokens per crop
+  const int tt = tokens + (cfg.pooling == UITK_POOL_TOKEN ? 1 : 0);    // rows per crop (cls row first)
   const int64_t RR = a.B * crops;
-  const int64_t M64 = RR * tokens;
+  const int64_t M64 = RR * tt;
   UITK_REQUIRE(M64 < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call (%lld); chunk the batch", (long long)M64);
   UITK_REQUIRE(cfg.outputdim <= 768, UITK_EINVAL, "outputdim %d > 768 unsupported by the head kernel", cfg.outputdim);
   UITK_REQUIRE(t_n <= cfg.grid_t, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
-  const int M = (int)M64;
+  UITK_REQUIRE(a.cond_used == nullptr, UITK_EINVAL, "uitk_encoder_fixup is implemented by the tensor-core configuration only");
+  const int M = (int)M64, Mp = (int)(RR * tokens);
 
-  const EncoderLayout lay = make_encoder_layout(cfg.depth, cfg.outputdim, cfg.grid_t);
+  const EncoderLayout lay = make_encoder_layout(cfg);
   // the fp32 section starts right after the header (pack.cu)
   const float* W = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(a.blob) + sizeof(BlobHeader));
+  const bool full = cfg.attention == UITK_ATTN_FULL;
+  const int qkv_n = lay.qkv_n, inner = lay.inner;
 
   unsigned char* ws = reinterpret_cast<unsigned char*>(a.ws);
   float* x = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 128 * 4, 256);
-  float* qkv = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 96 * 4, 256);
-  float* o = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * 32 * 4, 256);
+  float* qkv = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * qkv_n * 4, 256);
+  float* o = reinterpret_cast<float*>(ws); ws += align_up((size_t)M * inner * 4, 256);
   float* h = reinterpret_cast<float*>(ws);
-  UITK_REQUIRE(encoder_fp32_workspace_bytes(M) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
-               encoder_fp32_workspace_bytes(M), a.ws_bytes);
+  UITK_REQUIRE(encoder_fp32_workspace_bytes(cfg, M) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
+               encoder_fp32_workspace_bytes(cfg, M), a.ws_bytes);
 
   cudaStream_t s = a.stream;
   const int mb = (M + BM - 1) / BM;
   GemmParams p{};
-  p.M = M;
+  p.M = Mp;
   // ---- patch embed
   p.K = 256; p.Wt = W + lay.patch_wt; p.ldw = 128; p.bias = W + lay.patch_b; p.C = x; p.ldc = 128;
   p.db = a.db; p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
-  p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift; p.max_pow = a.max_pow;
+  p.bn_scale = W + (feat ? lay.ident_scale : lay.bn_scale); p.bn_shift = W + (feat ? lay.ident_shift : lay.bn_shift);
+  p.max_pow = a.max_pow; p.no_clamp = feat ? 1 : 0;
   p.time_pos = W + lay.time_pos; p.freq_pos = W + lay.freq_pos;
-  gemm_kernel<128, PRO_PATCH, EPI_PATCH><<<dim3(mb, 1), 256, 0, s>>>(p);
+  p.out_tt = tt; p.out_off = tt - tokens;
+  gemm_kernel<128, PRO_PATCH, EPI_PATCH><<<dim3((Mp + BM - 1) / BM, 1), 256, 0, s>>>(p);
+  int launches = 1;
+  if (tt != tokens) {
+    cls_fill_kernel<<<(unsigned)((RR * 128 + 255) / 256), 256, 0, s>>>(x, (int)RR, tt, W + lay.cls_row);
+    ++launches;
+  }
 
   for (int i = 0; i < cfg.depth; ++i) {
     const float* Wb = W + lay.blocks + (size_t)i * lay.block_stride;
     GemmParams g{};
     g.M = M;
     // LN1 + qkv
-    g.A = x; g.lda = 128; g.K = 128; g.Wt = Wb + lay.blk.qkv_wt; g.ldw = 96; g.bias = Wb + lay.blk.qkv_b;
-    g.C = qkv; g.ldc = 96; g.ln_w = Wb + lay.blk.ln1_w; g.ln_b = Wb + lay.blk.ln1_b; g.ln_eps = 1e-6f;
-    gemm_kernel<96, PRO_LN, EPI_BIAS><<<dim3(mb, 1), 256, 0, s>>>(g);
-    attention_kernel<<<(unsigned)((RR + 3) / 4), 256, 0, s>>>(qkv, o, (int)RR, tokens, 0.125f);
+    g.A = x; g.lda = 128; g.K = 128; g.Wt = Wb + lay.blk.qkv_wt; g.ldw = qkv_n; g.bias = Wb + lay.blk.qkv_b;
+    g.C = qkv; g.ldc = qkv_n; g.ln_w = Wb + lay.blk.ln1_w; g.ln_b = Wb + lay.blk.ln1_b; g.ln_eps = 1e-6f;
+    if (full) {
+      gemm_kernel<128, PRO_LN, EPI_BIAS><<<dim3(mb, 3), 256, 0, s>>>(g);
+      attention_kernel<64, 1><<<(unsigned)RR, 64, 0, s>>>(qkv, o, (int)RR, tt, 0.125f);           // (128 // 2) ** -0.5
+    } else {
+      gemm_kernel<96, PRO_LN, EPI_BIAS><<<dim3(mb, 1), 256, 0, s>>>(g);
+      attention_kernel<16, 4><<<(unsigned)((RR + 3) / 4), 256, 0, s>>>(qkv, o, (int)RR, tt, 0.125f);  // scale from the un-bottlenecked head dim (Q3)
+    }
     // proj + residual
-    g.A = o; g.lda = 32; g.K = 32; g.Wt = Wb + lay.blk.proj_wt; g.ldw = 128; g.bias = Wb + lay.blk.proj_b;
+    g.A = o; g.lda = inner; g.K = inner; g.Wt = Wb + lay.blk.proj_wt; g.ldw = 128; g.bias = Wb + lay.blk.proj_b;
     g.C = x; g.ldc = 128;
     gemm_kernel<128, PRO_PLAIN, EPI_BIAS_RESID><<<dim3(mb, 1), 256, 0, s>>>(g);
-    // LN2 + fc1 + ReLU
+    // LN2 + fc1 + activation
     g.A = x; g.lda = 128; g.K = 128; g.Wt = Wb + lay.blk.fc1_wt; g.ldw = 384; g.bias = Wb + lay.blk.fc1_b;
     g.C = h; g.ldc = 384; g.ln_w = Wb + lay.blk.ln2_w; g.ln_b = Wb + lay.blk.ln2_b;
-    gemm_kernel<128, PRO_LN, EPI_BIAS_RELU><<<dim3(mb, 3), 256, 0, s>>>(g);
+    if (cfg.act == UITK_ACT_GELU) gemm_kernel<128, PRO_LN, EPI_BIAS_GELU><<<dim3(mb, 3), 256, 0, s>>>(g);
+    else gemm_kernel<128, PRO_LN, EPI_BIAS_RELU><<<dim3(mb, 3), 256, 0, s>>>(g);
     // fc2 + residual
     g.A = h; g.lda = 384; g.K = 384; g.Wt = Wb + lay.blk.fc2_wt; g.ldw = 128; g.bias = Wb + lay.blk.fc2_b;
     g.C = x; g.ldc = 128;
     gemm_kernel<128, PRO_PLAIN, EPI_BIAS_RESID><<<dim3(mb, 1), 256, 0, s>>>(g);
   }
-  head_kernel<false><<<(unsigned)a.B, 256, 0, s>>>(x, crops, tokens, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w, W + lay.hln_b,
-                                            W + lay.head_wt, W + lay.head_b, cfg.outputdim, lay.outputdim_padded,
-                                            a.eval_avg, a.probs);
-  count_launches(2 + 5 * cfg.depth);
+  count_launches(launches + 5 * cfg.depth);
+  UITK_CHECK_CUDA(cudaGetLastError());
+  if (feat) return launch_final_ln(x, RR, tt, t_n, t_n, W + lay.norm_w, W + lay.norm_b, a.features_out, s);
+  head_kernel<true><<<(unsigned)a.B, 256, 0, s>>>(x, crops, tt, cfg.pooling, t_n, W + lay.norm_w, W + lay.norm_b, W + lay.hln_w,
+                                                  W + lay.hln_b, W + lay.head_wt, W + lay.head_b, cfg.outputdim, lay.outputdim_padded,
+                                                  a.eval_avg, a.probs);
+  count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;
 }
@@ -382,7 +512,9 @@ constexpr int kHeadClips = 8;
 __global__ void __launch_bounds__(256) head_pooled_kernel(const float* __restrict__ pooled, long long B, int crops,
                                                           const float* __restrict__ hln_w, const float* __restrict__ hln_b,
                                                           const float* __restrict__ head_wt, const float* __restrict__ head_b,
-                                                          int outputdim, int ld_head, int eval_max, float* __restrict__ probs) {
+                                                          int outputdim, int ld_head, int eval_max, float* __restrict__ probs,
+                                                          const uint32_t* c_true, const uint32_t* c_used, const uint32_t* c_min) {
+  if (c_used != nullptr && !fixup_needed(c_true, c_used, c_min)) return;      // uitk_encoder_fixup: nothing could differ
   __shared__ __align__(16) float pn[kHeadClips][128];      // normalised features
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long b0 = (long long)blockIdx.x * kHeadClips;
@@ -464,7 +596,9 @@ constexpr int kHM = 64, kHN = 64, kHLd = 132;
 __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ pooled, int B, const float* __restrict__ hln_w,
                                                         const float* __restrict__ hln_b, const float* __restrict__ head_wt,
                                                         const float* __restrict__ head_b, int outputdim, int ld_head,
-                                                        float* __restrict__ probs) {
+                                                        float* __restrict__ probs, const uint32_t* c_true, const uint32_t* c_used,
+                                                        const uint32_t* c_min) {
+  if (c_used != nullptr && !fixup_needed(c_true, c_used, c_min)) return;      // uitk_encoder_fixup: nothing could differ
   extern __shared__ __align__(16) float hs[];
   float* As = hs;                      // [64][132] normalised features
   float* Ws = hs + kHM * kHLd;         // [128][64] weight tile (k-major rows)
@@ -530,21 +664,23 @@ __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict_
 }  // namespace
 
 int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim,
-                       int eval_max, float* probs, cudaStream_t s) {
+                       int eval_max, float* probs, cudaStream_t s, const uint32_t* c_true, const uint32_t* c_used,
+                       const uint32_t* c_min) {
   if (crops == 1 && B < (1ll << 31) - 256) {
     // single crop: one tiled fp32 GEMM [B,128] x [128,outputdim] with the head LayerNorm as prologue and the sigmoid as
     // epilogue (every weight tile fetched from L2 feeds 128 clips)
     const int smem = (kHM * kHLd + 128 * kHN) * (int)sizeof(float);        // 66.5 KB
     UITK_CHECK_CUDA(cudaFuncSetAttribute(head_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     head_gemm_kernel<<<dim3((unsigned)((B + kHM - 1) / kHM), (unsigned)((outputdim + kHN - 1) / kHN)), 256, smem, s>>>(
-        pooled, (int)B, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, probs);
+        pooled, (int)B, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, probs,
+        c_true, c_used, c_min);
     count_launches(1);
     UITK_CHECK_CUDA(cudaGetLastError());
     return UITK_OK;
   }
   head_pooled_kernel<<<(unsigned)((B + kHeadClips - 1) / kHeadClips), 256, 0, s>>>(
       pooled, (long long)B, crops, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded,
-      eval_max, probs);
+      eval_max, probs, c_true, c_used, c_min);
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;

@@ -95,10 +95,12 @@ struct TcParams {
   const float* bn_scale; const float* bn_shift;
   const float* norm_w; const float* norm_b;
   const float* db; const uint32_t* max_pow;
-  int T, crops, tokens, t_n, target;
+  int T, crops, tokens, t_n, target;   // tokens = 24 row SLOTS per clip-crop (4 mel bands x 6 time slots); t_n = valid time patches
   int RR, G, num_tiles, depth;
+  int no_clamp;    // input is an already normalised spectrogram (uitk_forward_features): no top-dB clamp
   float* pooled;   // [RR][128]
-  float* dbg_x;    // optional [RR*tokens][128]: residual stream after the last block (pre final LN)
+  float* dbg_x;    // optional [RR*24][128]: residual stream after the last block (pre final LN), slot layout
+  const uint32_t* c_used; const uint32_t* c_min;   // uitk_encoder_fixup: return at once unless fixup_needed(max_pow, c_used, c_min)
 };
 
 // Optional in-kernel timeline (build with -DUITK_TRACE): thread 0 of CTA 0 and its MMA-issuer thread stamp
@@ -240,7 +242,14 @@ __device__ __forceinline__ uint4 relu_pack8(const float* v) {
   return o;
 }
 
+// kMasked = false: the native geometry (1 s clips: 6 time patches, all 24 token slots live).
+// kMasked = true : clips of 2400 .. 15 359 samples (1 .. 5 time patches).  The tile keeps the 24-slot layout (slot = band * 6 +
+//   tau) so that every offset, the position table and the 5-clips-per-tile packing stay as they are; slots with tau >= t_n
+//   carry a zero patch, are masked out of every softmax (probability exactly 0) and out of the token mean.  Wasted rows, but
+//   the clip runs on the tensor cores instead of the 33x slower fp32 CUDA-core kernels.
+template <bool kMasked>
 __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams p) {
+  if (p.c_used != nullptr && !fixup_needed(p.max_pow, p.c_used, p.c_min)) return;   // uniform: before any allocation / barrier
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
@@ -474,8 +483,9 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       ++sig;
     };
 
-    const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
-    const int tokens = p.tokens;          // 24: the kernel is only launched for the 24-token geometry (run_encoder_tc)
+    const float cutoff = p.no_clamp ? -INFINITY : 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*p.max_pow), 1e-10f)) - 120.f;
+    const int tokens = p.tokens;          // 24 slots per clip-crop
+    const int t_n = kMasked ? p.t_n : 6;  // valid time patches (slots with tau >= t_n are masked)
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int rr0 = tile * p.G;
@@ -515,15 +525,18 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) val[u][j] = __ldg(src + 32 * j);
+            for (int j = 0; j < 3; ++j) val[u][j] = (!kMasked || lane + 32 * j < 16 * t_n) ? __ldg(src + 32 * j) : 0.f;
             src += p.T;
           }
           unsigned char* d = lane_dst + g * (24 * 16);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-              *reinterpret_cast<__nv_bfloat16*>(d + u * 4096 + j * 32) = __float2bfloat16_rn(fmaf(fmaxf(val[u][j], cutoff), sc[u], sh[u]));
+            for (int j = 0; j < 3; ++j) {
+              const float y = fmaf(fmaxf(val[u][j], cutoff), sc[u], sh[u]);
+              *reinterpret_cast<__nv_bfloat16*>(d + u * 4096 + j * 32) =
+                  __float2bfloat16_rn((!kMasked || lane + 32 * j < 16 * t_n) ? y : 0.f);       // masked slots: zero patch
+            }
         }
         signal_ready();
       }
@@ -616,6 +629,13 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 #pragma unroll
                   for (int i = 0; i < 16; ++i) sv[i] = t[i];
                 }
+              }
+            }
+            if (kMasked) {   // key slot kc = i (hsel 0) / 16 + i (hsel 1) is live iff its time index kc % 6 < t_n
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int tau = hsel == 0 ? i % 6 : (16 + i) % 6;
+                if (tau >= t_n) sv[i] = -INFINITY;                        // every half row keeps a live key (slots 0 and 18)
               }
             }
             // hsel 0 owns keys 0..15 of the clip, hsel 1 keys 16..23 (sv[8..15] unused there); tree reductions for ILP
@@ -719,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         float* Y = reinterpret_cast<float*>(smem + OFF_A);
         float mean, rstd;
         row_stats(tx, hsel, r, 1e-6f, part, mean, rstd);
-        const float invn = 1.f / (float)tokens;
+        const float invn = 1.f / (float)(4 * t_n);
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           if (hsel == pass) {
@@ -747,6 +767,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           for (int g = tid >> 6; g < g_cnt; g += 4) {
             float acc = 0.f;
             for (int t = 0; t < tokens; ++t) {
+              if (kMasked && t % 6 >= t_n) continue;
               const int row = g * tokens + t;
               acc += Y[row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3))];
             }
@@ -791,52 +812,57 @@ size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows) {
 }
 
 int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W, const EncoderLayout& lay, int outputdim, int eval_max,
-                       float* probs, cudaStream_t s);
+                       float* probs, cudaStream_t s, const uint32_t* c_true, const uint32_t* c_used, const uint32_t* c_min);
 
 int run_encoder_tc(const EncoderArgs& a) {
   const uitk_encoder_cfg& cfg = *a.cfg;
-  const int crops = crops_for(a.T, a.target_length);
+  const bool feat = a.features_out != nullptr;
+  const int crops = feat ? 1 : crops_for(a.T, a.target_length);
   const int t_n = time_patches_for(a.T, a.target_length);
-  const int tokens = 4 * t_n;
+  constexpr int kSlots24 = 24;                  // row slots per clip-crop: 4 mel bands x 6 time slots, t_n of them live per band
   const int64_t RR = a.B * crops;
-  // The megakernel is built for the model's native geometry (24 tokens per crop = 5 crops per 128-row tile; every clip of
-  // >= 1 s).  Shorter clips (4..20 tokens) take the unfused fp32 CUDA-core kernels: a GPU path chosen by shape, with more
-  // precision than asked for; uitk_encoder_workspace_bytes() accounts for it.
-  if (tokens != 24) return run_encoder_fp32(a);
-  UITK_REQUIRE(RR * tokens < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call; chunk the batch");
-  UITK_REQUIRE(t_n <= cfg.grid_t, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
-  const EncoderLayout lay = make_encoder_layout(cfg.depth, cfg.outputdim, cfg.grid_t);
+  UITK_REQUIRE(RR * kSlots24 < (1ll << 31) - 256, UITK_EINVAL, "too many token rows for one call; chunk the batch");
+  UITK_REQUIRE(t_n >= 1 && t_n <= cfg.grid_t && t_n <= 6, UITK_EINVAL, "%d time patches exceed time_pos_embed length %d", t_n, cfg.grid_t);
+  const EncoderLayout lay = make_encoder_layout(cfg);
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.blob);
   const float* W = reinterpret_cast<const float*>(blob + sizeof(BlobHeader));
   const size_t bf16_off = sizeof(BlobHeader) + align_up(lay.total_floats * sizeof(float), 1024);
 
-  UITK_REQUIRE(encoder_tc_workspace_bytes(RR, RR * tokens) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
-               encoder_tc_workspace_bytes(RR, RR * tokens), a.ws_bytes);
+  UITK_REQUIRE(encoder_tc_workspace_bytes(RR, RR * kSlots24) <= a.ws_bytes, UITK_ENOSPACE, "workspace too small: need %zu, have %zu",
+               encoder_tc_workspace_bytes(RR, RR * kSlots24), a.ws_bytes);
   unsigned char* ws = reinterpret_cast<unsigned char*>(a.ws);
   float* dbg_x = reinterpret_cast<float*>(ws);
-  float* pooled = reinterpret_cast<float*>(ws + align_up((size_t)RR * tokens * 128 * 4, 256));
+  float* pooled = reinterpret_cast<float*>(ws + align_up((size_t)RR * kSlots24 * 128 * 4, 256));
 
   TcParams p{};
   p.wts = blob + bf16_off;
   p.pos_tab = W + lay.pos_tab;
-  p.bn_scale = W + lay.bn_scale; p.bn_shift = W + lay.bn_shift;
+  p.bn_scale = W + (feat ? lay.ident_scale : lay.bn_scale); p.bn_shift = W + (feat ? lay.ident_shift : lay.bn_shift);
   p.norm_w = W + lay.norm_w; p.norm_b = W + lay.norm_b;
-  p.db = a.db; p.max_pow = a.max_pow;
-  p.T = (int)a.T; p.crops = crops; p.tokens = tokens; p.t_n = t_n; p.target = a.target_length;
-  p.RR = (int)RR; p.G = 128 / tokens; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;
+  p.db = a.db; p.max_pow = a.max_pow; p.no_clamp = feat ? 1 : 0;
+  p.T = (int)a.T; p.crops = crops; p.tokens = kSlots24; p.t_n = t_n; p.target = a.target_length;
+  p.RR = (int)RR; p.G = 128 / kSlots24; p.num_tiles = (int)((RR + p.G - 1) / p.G); p.depth = cfg.depth;
   p.pooled = pooled;
-  p.dbg_x = (a.debug_taps & 1) ? dbg_x : nullptr;
+  p.dbg_x = (feat || (a.debug_taps & 1)) ? dbg_x : nullptr;
+  p.c_used = a.cond_used; p.c_min = a.cond_min;
 
   int dev = 0, sms = 0;
   UITK_CHECK_CUDA(cudaGetDevice(&dev));
   UITK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int resident = 2 * sms;                 // two CTAs per SM
   const int grid = p.num_tiles < resident ? p.num_tiles : resident;
-  encoder_tc_kernel<<<grid, kThreads, kSmemBytes, a.stream>>>(p);
+  if (t_n == 6) {
+    UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    encoder_tc_kernel<false><<<grid, kThreads, kSmemBytes, a.stream>>>(p);
+  } else {
+    UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    encoder_tc_kernel<true><<<grid, kThreads, kSmemBytes, a.stream>>>(p);
+  }
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
-  return launch_head_pooled(pooled, a.B, crops, W, lay, cfg.outputdim, a.eval_avg, a.probs, a.stream);
+  if (feat)   // tokens after the final LayerNorm, compacted from the 24-slot tile layout (uit.py:395)
+    return launch_final_ln(dbg_x, RR, kSlots24, t_n, 6, W + lay.norm_w, W + lay.norm_b, a.features_out, a.stream);
+  return launch_head_pooled(pooled, a.B, crops, W, lay, cfg.outputdim, a.eval_avg, a.probs, a.stream, a.max_pow, a.cond_used, a.cond_min);
 }
 
 }  // namespace uitk

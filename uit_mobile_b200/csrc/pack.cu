@@ -30,9 +30,12 @@ static size_t take(size_t& cur, size_t n) {
   return off;
 }
 
-EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
+EncoderLayout make_encoder_layout(const uitk_encoder_cfg& cfg) {
+  const int depth = cfg.depth, outputdim = cfg.outputdim, grid_t = cfg.grid_t;
   EncoderLayout l{};
   l.depth = depth; l.outputdim = outputdim; l.grid_t = grid_t;
+  l.qkv_n = cfg.attention == UITK_ATTN_FULL ? 384 : 96;
+  l.inner = cfg.attention == UITK_ATTN_FULL ? 128 : 32;
   l.outputdim_padded = (outputdim + 127) / 128 * 128;   // zero-padded to whole 128-column GEMM tiles
   size_t cur = 0;
   l.bn_scale = take(cur, 64); l.bn_shift = take(cur, 64);
@@ -42,12 +45,14 @@ EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
   l.hln_w = take(cur, 128); l.hln_b = take(cur, 128);
   l.cb_final = take(cur, 128);
   l.pos_tab = take(cur, 24 * 128);
+  l.cls_row = take(cur, 128);
+  l.ident_scale = take(cur, 64); l.ident_shift = take(cur, 64);
   l.head_wt = take(cur, (size_t)128 * l.outputdim_padded); l.head_b = take(cur, l.outputdim_padded);
   l.blocks = cur;
   size_t b = 0;
   l.blk.ln1_w = take(b, 128); l.blk.ln1_b = take(b, 128);
-  l.blk.qkv_wt = take(b, 128 * 96); l.blk.qkv_b = take(b, 96);
-  l.blk.proj_wt = take(b, 32 * 128); l.blk.proj_b = take(b, 128);
+  l.blk.qkv_wt = take(b, (size_t)128 * l.qkv_n); l.blk.qkv_b = take(b, l.qkv_n);
+  l.blk.proj_wt = take(b, (size_t)l.inner * 128); l.blk.proj_b = take(b, 128);
   l.blk.ln2_w = take(b, 128); l.blk.ln2_b = take(b, 128);
   l.blk.fc1_wt = take(b, 128 * 384); l.blk.fc1_b = take(b, 384);
   l.blk.fc2_wt = take(b, 384 * 128); l.blk.fc2_b = take(b, 128);
@@ -56,17 +61,17 @@ EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t) {
   return l;
 }
 
-// Order of h_tensors[] (state_dict keys).  Dead keys for pooling='mean' (cls_token,
-// token_pos_embed; Q4), the front-end buffers and num_batches_tracked are not passed.
+// Order of h_tensors[] (state_dict keys).  The front-end buffers and num_batches_tracked are not passed;
+// cls_token / token_pos_embed are dead for pooling='mean' | 'dm' (Q4) and live for pooling='token'.
 static const char* kFixedNames[] = {
     "init_bn.1.weight", "init_bn.1.bias", "init_bn.1.running_mean", "init_bn.1.running_var",
     "patch_embed.proj.weight", "patch_embed.proj.bias", "time_pos_embed", "freq_pos_embed",
     "norm.weight", "norm.bias", "outputlayer.0.weight", "outputlayer.0.bias",
-    "outputlayer.1.weight", "outputlayer.1.bias"};
+    "outputlayer.1.weight", "outputlayer.1.bias", "cls_token", "token_pos_embed"};
 static const char* kBlockNames[] = {
     "norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
     "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"};
-constexpr int kNumFixed = 14, kNumBlock = 12;
+constexpr int kNumFixed = 16, kNumBlock = 12;
 
 static void transpose_into(float* dst, const float* w, int out_f, int in_f, int ld_dst) {
   // torch Linear weight [out_f][in_f] -> Wt[in_f][ld_dst]
@@ -125,6 +130,7 @@ uint64_t uitk_kernel_launches(void) { return get_launches(); }
 int64_t uitk_num_frames(int64_t L) { return 1 + L / UITK_HOP; }
 int uitk_num_crops(int64_t T, int target_length) { return crops_for(T, target_length); }
 int uitk_tokens_per_crop(int64_t T, int target_length) { return 4 * time_patches_for(T, target_length); }
+int uitk_tokens_total(const uitk_encoder_cfg* cfg, int64_t T, int target_length) { return cfg ? tokens_total_for(*cfg, T, target_length) : 0; }
 
 size_t uitk_frontend_blob_bytes(const float* h_fb) { (void)h_fb; return sizeof(FrontendBlob); }
 
@@ -194,14 +200,18 @@ static int check_cfg(const uitk_encoder_cfg* cfg) {
   UITK_REQUIRE(cfg->outputdim >= 1 && cfg->outputdim <= 768, UITK_EINVAL, "outputdim %d out of range [1,768]", cfg->outputdim);
   UITK_REQUIRE(cfg->grid_t >= 1 && cfg->grid_t <= 6, UITK_EINVAL, "grid_t %d out of range [1,6]", cfg->grid_t);
   UITK_REQUIRE(cfg->precision == UITK_PREC_FP32 || cfg->precision == UITK_PREC_BF16, UITK_EINVAL, "bad precision %d", cfg->precision);
+  UITK_REQUIRE(cfg->attention == UITK_ATTN_BNECK || cfg->attention == UITK_ATTN_FULL, UITK_EINVAL, "bad attention type %d", cfg->attention);
+  UITK_REQUIRE(cfg->act == UITK_ACT_RELU || cfg->act == UITK_ACT_GELU, UITK_EINVAL, "bad activation %d", cfg->act);
+  UITK_REQUIRE(cfg->pooling >= UITK_POOL_MEAN && cfg->pooling <= UITK_POOL_DM, UITK_EINVAL, "bad pooling %d", cfg->pooling);
+  UITK_REQUIRE(cfg->reserved == 0, UITK_EINVAL, "cfg.reserved must be 0");
   return UITK_OK;
 }
 
 size_t uitk_encoder_blob_bytes(const uitk_encoder_cfg* cfg) {
   if (check_cfg(cfg) != UITK_OK) return 0;
-  const EncoderLayout l = make_encoder_layout(cfg->depth, cfg->outputdim, cfg->grid_t);
+  const EncoderLayout l = make_encoder_layout(*cfg);
   size_t n = sizeof(BlobHeader) + fp32_section_bytes(l);
-  if (cfg->precision == UITK_PREC_BF16) n += encoder_tc_bf16_section_bytes(cfg->depth);
+  if (tc_config(*cfg)) n += encoder_tc_bf16_section_bytes(cfg->depth);
   return n;
 }
 
@@ -213,7 +223,8 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
   UITK_REQUIRE(blob_bytes >= need, UITK_ENOSPACE, "encoder blob needs %zu bytes, have %zu", need, blob_bytes);
   for (int i = 0; i < uitk_encoder_num_tensors(cfg->depth); ++i)
     UITK_REQUIRE(t[i], UITK_EINVAL, "tensor %d (%s) is null", i, uitk_encoder_tensor_name(cfg->depth, i));
-  const EncoderLayout l = make_encoder_layout(cfg->depth, cfg->outputdim, cfg->grid_t);
+  const EncoderLayout l = make_encoder_layout(*cfg);
+  const bool tc = tc_config(*cfg);
   memset(h_blob, 0, need);
   BlobHeader* hdr = reinterpret_cast<BlobHeader*>(h_blob);
   hdr->magic = kEncoderMagic; hdr->depth = cfg->depth; hdr->outputdim = cfg->outputdim; hdr->grid_t = cfg->grid_t;
@@ -238,12 +249,14 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
   memcpy(W + l.hln_w, t[10], 128 * sizeof(float)); memcpy(W + l.hln_b, t[11], 128 * sizeof(float));
   transpose_into(W + l.head_wt, t[12], cfg->outputdim, 128, l.outputdim_padded);
   memcpy(W + l.head_b, t[13], cfg->outputdim * sizeof(float));
+  for (int c = 0; c < 128; ++c) W[l.cls_row + c] = t[14][c] + t[15][c];      // cls_token + token_pos_embed (uit.py:390-391)
+  for (int m = 0; m < 64; ++m) { W[l.ident_scale + m] = 1.f; W[l.ident_shift + m] = 0.f; }
   for (int i = 0; i < cfg->depth; ++i) {
     const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
     float* Wb = W + l.blocks + (size_t)i * l.block_stride;
     memcpy(Wb + l.blk.ln1_w, b[0], 128 * 4); memcpy(Wb + l.blk.ln1_b, b[1], 128 * 4);
-    transpose_into(Wb + l.blk.qkv_wt, b[2], 96, 128, 96); memcpy(Wb + l.blk.qkv_b, b[3], 96 * 4);
-    transpose_into(Wb + l.blk.proj_wt, b[4], 128, 32, 128); memcpy(Wb + l.blk.proj_b, b[5], 128 * 4);
+    transpose_into(Wb + l.blk.qkv_wt, b[2], l.qkv_n, 128, l.qkv_n); memcpy(Wb + l.blk.qkv_b, b[3], l.qkv_n * 4);
+    transpose_into(Wb + l.blk.proj_wt, b[4], 128, l.inner, 128); memcpy(Wb + l.blk.proj_b, b[5], 128 * 4);
     memcpy(Wb + l.blk.ln2_w, b[6], 128 * 4); memcpy(Wb + l.blk.ln2_b, b[7], 128 * 4);
     transpose_into(Wb + l.blk.fc1_wt, b[8], 384, 128, 384); memcpy(Wb + l.blk.fc1_b, b[9], 384 * 4);
     transpose_into(Wb + l.blk.fc2_wt, b[10], 128, 384, 128); memcpy(Wb + l.blk.fc2_b, b[11], 128 * 4);
@@ -251,14 +264,14 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
   // cb = running sum of all proj / fc2 biases (cb_final keeps the blob layout of earlier versions; no kernel reads it)
   std::vector<float> cb(128, 0.f);
   unsigned char* sec = reinterpret_cast<unsigned char*>(h_blob) + sizeof(BlobHeader) + fp32_section_bytes(l);
-  if (cfg->precision == UITK_PREC_BF16) {
+  if (tc) {
     hdr->bf16_offset = sizeof(BlobHeader) + fp32_section_bytes(l);
     for (int c = 0; c < 4; ++c)                                                          // patch weight, K quarters
       pack_kmajor(reinterpret_cast<uint16_t*>(sec + (size_t)c * 16384), t[4], 256, 0, 128, c * 64, 64);
   }
   for (int i = 0; i < cfg->depth; ++i) {
     const float* const* b = t + kNumFixed + (size_t)i * kNumBlock;
-    if (cfg->precision == UITK_PREC_BF16) {
+    if (tc) {
       unsigned char* blk = sec + 65536 + (size_t)i * encoder_tc_block_bytes();   // after the 4 x 16 KB patch chunks
       // LayerNorm affine folded into the consuming Linear: W' = W diag(gamma), b' = b + W beta (fp32, then bf16 for W')
       std::vector<float> wq(96 * 128), w1f(384 * 128), bq(96), b1f(384);
@@ -303,10 +316,12 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
     for (int c = 0; c < 128; ++c) cb[c] = (cb[c] + b[5][c]) + b[11][c];
   }
   memcpy(W + l.cb_final, cb.data(), 128 * 4);
-  if (cfg->grid_t >= 6)
-    for (int tok = 0; tok < 24; ++tok)
-      for (int c = 0; c < 128; ++c)
-        W[l.pos_tab + (size_t)tok * 128 + c] = (t[5][c] + t[6][(size_t)c * cfg->grid_t + tok % 6]) + t[7][(size_t)c * 4 + tok / 6];
+  // tensor-core tile: 24 row slots per clip-crop, slot = band * 6 + tau; time slots beyond time_pos_embed are never live
+  for (int tok = 0; tok < 24; ++tok)
+    for (int c = 0; c < 128; ++c) {
+      const float tp = tok % 6 < cfg->grid_t ? t[6][(size_t)c * cfg->grid_t + tok % 6] : 0.f;
+      W[l.pos_tab + (size_t)tok * 128 + c] = (t[5][c] + tp) + t[7][(size_t)c * 4 + tok / 6];
+    }
   return UITK_OK;
 }
 

@@ -61,12 +61,15 @@ struct BlockOffsets {
 
 struct EncoderLayout {
   int depth, outputdim, grid_t;
+  int qkv_n, inner;                   // 96 / 32 (BNeckAttention) or 384 / 128 (Attention)
   size_t bn_scale, bn_shift;          // [64] folded eval BatchNorm
   size_t patch_wt, patch_b;           // [256][128], [128]
   size_t time_pos, freq_pos;          // [grid_t][128], [4][128]
   size_t norm_w, norm_b, hln_w, hln_b;
   size_t cb_final;                    // [128] sum of all proj/fc2 biases (kept for blob compatibility; unused)
   size_t pos_tab;                     // [24][128] conv bias + time_pos[tok % 6] + freq_pos[tok / 6] (tensor-core path, 24-token crops)
+  size_t cls_row;                     // [128] cls_token + token_pos_embed (pooling='token', uit.py:389-392)
+  size_t ident_scale, ident_shift;    // [64] ones / zeros: "input already normalised" (uitk_forward_features)
   size_t head_wt, head_b;             // [128][outputdim_padded], [outputdim_padded]
   int outputdim_padded;
   size_t blocks;                      // first block
@@ -75,7 +78,10 @@ struct EncoderLayout {
   size_t total_floats;
 };
 
-EncoderLayout make_encoder_layout(int depth, int outputdim, int grid_t);
+EncoderLayout make_encoder_layout(const uitk_encoder_cfg& cfg);
+inline bool tc_config(const uitk_encoder_cfg& c) {   // what the tensor-core megakernel implements
+  return c.precision == UITK_PREC_BF16 && c.attention == UITK_ATTN_BNECK && c.act == UITK_ACT_RELU && c.pooling == UITK_POOL_MEAN;
+}
 
 struct BlobHeader {
   int magic;        // 'UEN1'
@@ -118,7 +124,26 @@ struct EncoderArgs {
   size_t ws_bytes;
   cudaStream_t stream;
   int debug_taps;
+  // uitk_forward_features: db is an already normalised spectrogram (no clamp, no BatchNorm), no crops, and instead of the
+  // head the final-LayerNorm tokens [B][tokens_total][128] are written to features_out
+  float* features_out = nullptr;
+  // uitk_encoder_fixup: {max_pow (true), max_used, min_pow}; every kernel returns at once unless fixup_needed()
+  const uint32_t* cond_used = nullptr;
+  const uint32_t* cond_min = nullptr;
 };
+// Device-side decision of uitk_encoder_fixup (see include/uitk.h): same dB map as the kernels' cutoff.
+__device__ __forceinline__ bool fixup_needed(const uint32_t* max_true, const uint32_t* max_used, const uint32_t* min_pow) {
+  const uint32_t mt = *max_true, mu = *max_used;
+  if (mt == mu) return false;
+  const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(mt), 1e-10f)) - 120.f;
+  const float min_db = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*min_pow), 1e-10f));
+  return min_db < cutoff;
+}
+int launch_final_ln(const float* x, int64_t RR, int slots, int t_n, int slot_tn, const float* norm_w, const float* norm_b, float* out,
+                    cudaStream_t s);
+int launch_init_bn(const float* db, int64_t B, int64_t T, const float* scale, const float* shift, float* out, cudaStream_t s);
+int run_forward_head(const uitk_encoder_cfg& cfg, const void* blob, const float* tokens, int64_t B, int n_tokens, float* probs,
+                     cudaStream_t s);
 int run_encoder_fp32(const EncoderArgs& a);
 int run_encoder_tc(const EncoderArgs& a);
 int read_encoder_trace(long long* host_out, int which, int n);
@@ -126,6 +151,9 @@ int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float*
 size_t encoder_tc_bf16_section_bytes(int depth);
 size_t encoder_tc_block_bytes();
 size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows);
-size_t encoder_fp32_workspace_bytes(int64_t rows);   // rows = B * crops * tokens
+size_t encoder_fp32_workspace_bytes(const uitk_encoder_cfg& cfg, int64_t rows);   // rows = B * crops * tokens_total
+inline int tokens_total_for(const uitk_encoder_cfg& c, int64_t T, int target) {
+  return 4 * time_patches_for(T, target) + (c.pooling == UITK_POOL_TOKEN ? 1 : 0);
+}
 
 }  // namespace uitk

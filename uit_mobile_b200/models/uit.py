@@ -18,7 +18,9 @@ import torch.nn as nn
 
 from .. import _native as N
 
-__all__ = ["UITBase", "uit_xs", "uit_xxs", "uit_xxxs", "PRETRAINED_CHECKPOINTS"]
+__all__ = ["UITBase", "uit_xs", "uit_xxs", "uit_xxxs", "PRETRAINED_CHECKPOINTS", "audio_transformer_h128_d4_m3_relu",
+           "audio_transformer_h128_d4_m3", "audio_transformer_h128_d6_m3", "audio_transformer_h128_d6_m3_relu",
+           "audio_transformer_h128_d3_m3_bneck_v2_relu", "AudioPatchEmbed", "BNeckAttention", "Attention", "Mlp", "Block"]
 
 
 class _Holder(nn.Module):
@@ -59,6 +61,18 @@ class _BatchNorm(_Holder):
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
 
+class _InitBN(nn.Sequential):
+    """``init_bn`` of the reference (uit.py:310-313): Rearrange -> eval BatchNorm2d over the mel axis -> Rearrange.  Callable like
+    the reference's ([B, 1, 64, T] -> same shape) through the CUDA kernel; inside ``UITBase.forward`` it is fused into the
+    encoder's patch gather."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        owner = self.__dict__.get("_owner")
+        if owner is None or owner() is None:
+            raise RuntimeError("init_bn is bound to its UITBase model")
+        return owner()._init_bn(x)
+
+
 class _Conv(_Holder):
     def __init__(self, out_ch: int, k: int):
         super().__init__()
@@ -95,22 +109,35 @@ class BNeckAttention(_Holder):
         self.proj = _Linear(self.inner_dim, dim)
 
 
+class Attention(_Holder):
+    """uit.py:124-178 (causal=False): qkv dim -> 3 dim, heads of dim // num_heads."""
+
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.causal = False
+        self.qkv = _Linear(dim, dim * 3)
+        self.proj = _Linear(dim, dim)
+
+
 class Mlp(_Holder):
-    def __init__(self, dim: int, hidden: int):
+    def __init__(self, dim: int, hidden: int, act_layer=nn.ReLU):
         super().__init__()
         self.fc1 = _Linear(dim, hidden)
+        self.act = act_layer()
         self.fc2 = _Linear(hidden, dim)
 
 
 class Block(_Holder):
     """uit.py:206-248 with LayerScale / DropPath = Identity."""
 
-    def __init__(self, dim: int, num_heads: int, mlp_ratio: float):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float, act_layer=nn.ReLU, attention_type: str = "BNeckAttention"):
         super().__init__()
         self.norm1 = _LayerNorm(dim, 1e-6)
-        self.attn = BNeckAttention(dim, num_heads)
+        self.attn = {"BNeckAttention": BNeckAttention, "Attention": Attention}[attention_type](dim, num_heads)
         self.norm2 = _LayerNorm(dim, 1e-6)
-        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer)
 
 
 class _Spectrogram(_Holder):
@@ -224,7 +251,9 @@ def _logmel_sliding(front_end, stream: torch.Tensor, window: int = 16000, hop: i
     if n < window:
         raise ValueError("stream shorter than one window")
     W = (n - window) // hop + 1
-    if hop % 160 != 0 or window % 160 != 0:
+    if hop % 160 != 0 or window % 160 != 0 or hop // 160 > window // 160 - 3:
+        # no shared interior frames (hop not on the STFT grid), or windows so far apart that some stream frames belong to no
+        # window (they would still raise the batch-global top-dB maximum): every window runs its own front-end, read in place
         return front_end.logmel_unclamped(stream, ld=hop, B=W, L=window, max_pow=max_pow, min_pow=min_pow)
     l = N.lib()
     T = int(l.uitk_num_frames(window))
@@ -243,7 +272,9 @@ FrontEnd.logmel_sliding = _logmel_sliding
 
 
 class UITBase(nn.Module):
-    """uit.py:252-493, inference path only (eval mode, pooling='mean', BNeckAttention, ReLU MLP, init_bn)."""
+    """uit.py:252-493, inference path only (eval mode, init_bn).  The UiT-XS/XXS/XXXS configuration (BNeckAttention, ReLU MLP,
+    pooling='mean') runs on the tcgen05 megakernel when ``precision='bf16'``; the other variants of the class (full
+    ``Attention``, GELU, pooling='token' | 'dm') run on the fp32 CUDA-core kernels whatever ``precision`` says."""
 
     def __init__(self, outputdim=527, patch_size=16, patch_stride=16, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., init_bn: bool = True,
@@ -273,10 +304,12 @@ class UITBase(nn.Module):
         def need(cond, what):
             if not cond:
                 raise NotImplementedError(f"uit_mobile_b200 implements the UiT-XS/XXS/XXXS inference path only: {what}")
-        need(pooling == 'mean', f"pooling={pooling!r} (only 'mean')")
-        need(attention_type == 'BNeckAttention', f"attention_type={attention_type!r} (only 'BNeckAttention')")
+        if attention_type not in ('BNeckAttention', 'Attention'):
+            raise KeyError(attention_type)           # the reference looks the class up in globals() (uit.py:224): same error
         need(block_type == 'Block', f"block_type={block_type!r}")
-        need(act_layer is nn.ReLU, "act_layer must be nn.ReLU")
+        act_layer = act_layer or nn.GELU             # uit.py:338
+        need(act_layer in (nn.ReLU, nn.GELU), "act_layer must be nn.ReLU or nn.GELU")
+        self.attention_type, self.act_layer = attention_type, act_layer
         need(init_bn, "init_bn=False")
         need(embed_dim == 128 and num_heads == 2 and float(mlp_ratio) == 3.0, "embed_dim/num_heads/mlp_ratio != 128/2/3.0")
         need(patch_size == 16 and patch_stride == 16, "patch_size/stride != 16")
@@ -291,7 +324,9 @@ class UITBase(nn.Module):
         need(precision in N.PRECISIONS, f"precision={precision!r} (fp32 or bf16)")
 
         self.front_end = FrontEnd(MelSpectrogram(f_min, f_max, self.n_mels, n_fft), AmplitudeToDB(top_db=120))
-        self.init_bn = nn.Sequential(nn.Identity(), _BatchNorm(self.n_mels), nn.Identity())
+        self.init_bn = _InitBN(nn.Identity(), _BatchNorm(self.n_mels), nn.Identity())
+        import weakref
+        self.init_bn.__dict__["_owner"] = weakref.ref(self)
         self.patch_embed = AudioPatchEmbed((self.n_mels, target_length), patch_size, patch_stride, embed_dim)
         self.spectransforms = nn.Sequential() if spectransforms is None else spectransforms
         self.wavtransforms = nn.Sequential() if wavtransforms is None else wavtransforms
@@ -300,7 +335,7 @@ class UITBase(nn.Module):
         self.time_pos_embed = nn.Parameter(torch.randn(1, embed_dim, 1, self.patch_embed.grid_size[1]) * .02)
         self.freq_pos_embed = nn.Parameter(torch.randn(1, embed_dim, self.patch_embed.grid_size[0], 1) * .02)
         self.pos_drop = nn.Identity()
-        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio, act_layer, attention_type) for _ in range(depth)])
         self.norm = _LayerNorm(embed_dim, 1e-6)
         self.outputlayer = nn.Sequential(_LayerNorm(embed_dim, 1e-5), _Linear(embed_dim, outputdim))
         nn.init.normal_(self.cls_token, std=1e-6)
@@ -311,12 +346,12 @@ class UITBase(nn.Module):
     def no_weight_decay(self):
         return {'time_pos_embed', 'cls_token', 'freq_pos_embed', 'token_pos_embed'}
 
-    def load_state_dict(self, state_dict, strict=True):
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
         """uit.py:416-450: slice / bilinearly resize the positional embeddings when shapes differ."""
         if 'time_pos_embed' in state_dict and self.time_pos_embed.shape != state_dict['time_pos_embed'].shape:
             state_dict = dict(state_dict)
             self.change_pos_embedding(state_dict)
-        return super().load_state_dict(state_dict, strict=strict)
+        return super().load_state_dict(state_dict, strict=strict, **kwargs)
 
     def change_pos_embedding(self, state_dict):
         tt, tf = self.time_pos_embed.shape[-1], self.freq_pos_embed.shape[-2]
@@ -336,7 +371,9 @@ class UITBase(nn.Module):
 
     # ---- kernel plumbing -----------------------------------------------------------------------------------------
     def _cfg(self) -> N.EncoderCfg:
-        return N.EncoderCfg(self.depth, self.outputdim, self.patch_embed.grid_size[1], N.PRECISIONS[self.precision])
+        return N.EncoderCfg(self.depth, self.outputdim, self.patch_embed.grid_size[1], N.PRECISIONS[self.precision],
+                            N.ATTENTION[self.attention_type], N.ACT["relu" if self.act_layer is nn.ReLU else "gelu"],
+                            N.POOLING[self.pooling])
 
     def _encoder_blob(self, device: torch.device) -> torch.Tensor:
         """Pack the state_dict into the kernel layout (lazily; re-packed when any tensor changed)."""
@@ -360,8 +397,26 @@ class UITBase(nn.Module):
             self._packed = {"key": key, "blob": blob.to(device)}
         return self._packed["blob"]
 
-    def encode(self, db: torch.Tensor, max_pow: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """init_bn + crops + forward_features + forward_head on un-clamped log-mel (uit.py:460-492)."""
+    def _check_ready(self, t: torch.Tensor, what: str):
+        if self.training:
+            raise NotImplementedError("uit_mobile_b200 implements inference only: call model.eval() "
+                                      "(training branches of uit.py:453-459 are out of scope)")
+        if not t.is_cuda:
+            raise N.UitkError(f"{what}: UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
+
+    def encode(self, db: torch.Tensor, max_pow: torch.Tensor, out: Optional[torch.Tensor] = None, *,
+               fixup: Optional[tuple] = None, workspace_out: Optional[list] = None) -> torch.Tensor:
+        """init_bn + crops + forward_features + forward_head on un-clamped log-mel (uit.py:460-492).
+
+        ``fixup=(max_used, min_pow)`` turns the call into the device-conditional exact re-run of a speculative encode
+        (``uitk_encoder_fixup``); ``workspace_out`` (a list) receives the launch workspace (tests: debug taps)."""
+        self._check_ready(db, "encode")
+        if db.dtype != torch.float32 or db.dim() != 3 or db.shape[1] != 64 or not db.is_contiguous():
+            raise ValueError(f"db must be a contiguous float32 [B, 64, T] CUDA tensor, got {db.dtype} {tuple(db.shape)}")
+        words = (max_pow,) + (tuple(fixup) if fixup is not None else ())
+        for w in words:
+            if w.dtype != torch.int32 or w.device != db.device or w.numel() != 1:
+                raise ValueError("max_pow / fixup words must be one-element int32 tensors on the device of db")
         l = N.lib()
         B, _, T = db.shape
         cfg = self._cfg()
@@ -369,10 +424,10 @@ class UITBase(nn.Module):
         if out is None:
             probs = torch.empty((B, self.outputdim), dtype=torch.float32, device=db.device)
         else:
-            if tuple(out.shape) != (B, self.outputdim) or out.dtype != torch.float32 or not out.is_contiguous():
-                raise ValueError("out must be a contiguous float32 [B, outputdim] tensor")
+            if tuple(out.shape) != (B, self.outputdim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != db.device:
+                raise ValueError("out must be a contiguous float32 [B, outputdim] tensor on the device of db")
             probs = out
-        # launches are cut at multiples of the kernel's 128-row tile (5 clip-crops of 24 tokens): the tensor-core attention
+        # launches are cut at multiples of the kernel's 128-row tile (5 clip-crops of 24 token slots): the tensor-core attention
         # sums over a tile's keys, so a clip's rounding depends on its position inside the tile; tile-aligned cuts keep
         # chunked / sharded runs bit-identical to a single launch
         tile = self.tile_clips(T)
@@ -386,33 +441,105 @@ class UITBase(nn.Module):
                 if need == 0:
                     N.check(-1, "uitk_encoder_workspace_bytes")
                 if ws is None or ws.numel() < need:
-                    ws = torch.empty(need, dtype=torch.uint8, device=db.device)
-                N.check(l.uitk_encoder(C.byref(cfg), blob.data_ptr(), db[b0:b0 + nb].data_ptr(), nb, T, self.target_length,
-                                       1 if self.eval_avg == 'max' else 0, max_pow.data_ptr(), probs[b0:b0 + nb].data_ptr(),
-                                       ws.data_ptr(), ws.numel(), stream), "uitk_encoder")
-            self._last_workspace = ws
+                    ws = torch.empty(need, dtype=torch.uint8, device=db.device)     # stream-ordered caching allocator: not kept
+                if fixup is None:
+                    N.check(l.uitk_encoder(C.byref(cfg), blob.data_ptr(), db[b0:b0 + nb].data_ptr(), nb, T, self.target_length,
+                                           1 if self.eval_avg == 'max' else 0, max_pow.data_ptr(), probs[b0:b0 + nb].data_ptr(),
+                                           ws.data_ptr(), ws.numel(), stream), "uitk_encoder")
+                else:
+                    N.check(l.uitk_encoder_fixup(C.byref(cfg), blob.data_ptr(), db[b0:b0 + nb].data_ptr(), nb, T, self.target_length,
+                                                 1 if self.eval_avg == 'max' else 0, max_pow.data_ptr(), fixup[0].data_ptr(),
+                                                 fixup[1].data_ptr(), probs[b0:b0 + nb].data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                            "uitk_encoder_fixup")
+            if workspace_out is not None:
+                workspace_out.append(ws)
         return probs
 
-    def forward_features(self, x):
-        """Reference: uit.py:379-396 (tokens after the final LayerNorm).  The B200 path never materialises them: BatchNorm,
-        patch embedding, all blocks, the final norm and the token mean are one fused kernel (see ``encode``)."""
-        raise NotImplementedError("forward_features is fused into UITBase.encode() on the B200 path (no per-stage tensors); "
-                                  "use model(x) / model.encode(db, max_pow)")
+    def _init_bn(self, x: torch.Tensor) -> torch.Tensor:
+        """init_bn (uit.py:310-313, 460-462) on [B, 1, 64, T] (or [B, 64, T]): eval BatchNorm over the mel axis."""
+        self._check_ready(x, "init_bn")
+        shape = x.shape
+        if x.dtype != torch.float32 or x.dim() not in (3, 4) or shape[-2] != 64 or (x.dim() == 4 and shape[1] != 1):
+            raise ValueError(f"init_bn expects a float32 [B, 1, 64, T] spectrogram, got {x.dtype} {tuple(shape)}")
+        xc = x.reshape(shape[0], 64, shape[-1]).contiguous()
+        out = torch.empty_like(xc)
+        cfg = self._cfg()
+        with torch.cuda.device(x.device):
+            N.check(N.lib().uitk_init_bn(C.byref(cfg), self._encoder_blob(x.device).data_ptr(), xc.data_ptr(), xc.shape[0], xc.shape[2],
+                                         out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "uitk_init_bn")
+        return out.reshape(shape)
 
-    def forward_head(self, x):
-        """Reference: uit.py:398-412.  Fused into ``encode`` (head LayerNorm + Linear + sigmoid + crop reduction)."""
-        raise NotImplementedError("forward_head is fused into UITBase.encode() on the B200 path; use model(x)")
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """uit.py:379-396: normalised spectrogram crop [B, 1, 64, T] (T <= 16 * grid + 15) -> tokens [B, N, 128] after the final
+        LayerNorm (N = 4 * time patches, + the cls token for pooling='token').  One launch of the same kernels ``forward`` uses
+        (the tensor-core megakernel for the UiT configuration), stopped before the pooling."""
+        self._check_ready(x, "forward_features")
+        if x.dtype != torch.float32 or x.dim() not in (3, 4) or x.shape[-2] != 64 or (x.dim() == 4 and x.shape[1] != 1):
+            raise ValueError(f"forward_features expects a float32 [B, 1, 64, T] spectrogram, got {x.dtype} {tuple(x.shape)}")
+        B, T = x.shape[0], x.shape[-1]
+        xc = x.reshape(B, 64, T).contiguous()
+        l = N.lib()
+        cfg = self._cfg()
+        target = 16 * self.patch_embed.grid_size[1] + 15
+        if not (16 <= T <= target):
+            raise ValueError(f"forward_features takes 16..{target} frames (time_pos_embed has {self.patch_embed.grid_size[1]} entries), got {T}")
+        n_tok = int(l.uitk_tokens_total(C.byref(cfg), T, target))
+        out = torch.empty((B, n_tok, self.embed_dim), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
+        with torch.cuda.device(x.device):
+            need = l.uitk_forward_features_workspace_bytes(C.byref(cfg), B, T)
+            if need == 0:
+                N.check(-1, "uitk_forward_features_workspace_bytes")
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            N.check(l.uitk_forward_features(C.byref(cfg), self._encoder_blob(x.device).data_ptr(), xc.data_ptr(), B, T, out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream(x.device).cuda_stream),
+                    "uitk_forward_features")
+        return out
+
+    def forward_head(self, x: torch.Tensor) -> torch.Tensor:
+        """uit.py:398-412: tokens [B, N, 128] -> sigmoid scores [B, outputdim] (pooling 'mean' | 'token' | 'dm')."""
+        self._check_ready(x, "forward_head")
+        if x.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.embed_dim:
+            raise ValueError(f"forward_head expects float32 tokens [B, N, {self.embed_dim}], got {x.dtype} {tuple(x.shape)}")
+        xc = x.contiguous()
+        out = torch.empty((x.shape[0], self.outputdim), dtype=torch.float32, device=x.device)
+        cfg = self._cfg()
+        with torch.cuda.device(x.device):
+            N.check(N.lib().uitk_forward_head(C.byref(cfg), self._encoder_blob(x.device).data_ptr(), xc.data_ptr(), xc.shape[0], xc.shape[1],
+                                              out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "uitk_forward_head")
+        return out
 
     def tile_clips(self, T: int) -> int:
         """Clips per 128-row encoder tile for T frames: chunk / shard boundaries that are multiples of this (in clips)
-        reproduce a single launch bit for bit."""
-        l = N.lib()
-        rows_per_clip = int(l.uitk_num_crops(T, self.target_length)) * int(l.uitk_tokens_per_crop(T, self.target_length))
-        per_tile = 128 // int(l.uitk_tokens_per_crop(T, self.target_length))          # clip-crops per tile
-        crops = int(l.uitk_num_crops(T, self.target_length))
-        # smallest number of clips whose clip-crops fill whole tiles
-        import math
-        return per_tile // math.gcd(per_tile, crops) if rows_per_clip else 1
+        reproduce a single launch bit for bit.  The tile holds 5 clip-crops of 24 token slots for every clip length."""
+        crops = int(N.lib().uitk_num_crops(T, self.target_length))
+        return 5 // math.gcd(5, crops)
+
+    def _finish(self, db: torch.Tensor, words: torch.Tensor) -> torch.Tensor:
+        """Encoder + head given the un-clamped log-mel and the [max, min] power words of THIS rank's clips (Q2)."""
+        max_w, min_w = words[0:1], words[1:2]
+        if self.process_group is None:
+            return self.encode(db, max_w)
+        dist = torch.distributed
+        if not self._cfg().tensor_core:
+            # fp32 / variant kernels: the batch-global cutoff first (blocking all-reduce of one word), then the encoder
+            dist.all_reduce(max_w, op=dist.ReduceOp.MAX, group=self.process_group)
+            return self.encode(db, max_w)
+        # Sharded, tensor-core configuration: NO collective on the critical path.  Encode speculatively with the rank-local
+        # maximum while the all-reduce(MAX) of [max, -1 - min] (non-negative floats order like their int32 bit patterns) runs on
+        # the NCCL stream, then launch the device-conditional exact re-run: its kernels return at once unless this rank's
+        # cutoff was below the global one AND one of its values lies under the global cutoff (uitk_encoder_fixup).
+        g = torch.stack((words[0], -1 - words[1]))
+        work = dist.all_reduce(g, op=dist.ReduceOp.MAX, group=self.process_group, async_op=True)
+        probs = self.encode(db, max_w) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
+        work.wait()
+        if db.shape[0]:
+            self.encode(db, g[0:1], out=probs, fixup=(max_w, min_w))
+        return probs
+
+    def _new_words(self, device) -> torch.Tensor:
+        return torch.tensor([0, 0x7F800000], dtype=torch.int32, device=device)       # [max power bits, min power bits (+inf)]
 
     def forward(self, x: torch.Tensor, mixup=None) -> torch.Tensor:
         if self.training:
@@ -421,12 +548,17 @@ class UITBase(nn.Module):
         if self.eval_avg not in ('mean', 'max'):
             raise ValueError(f'Unknown Eval average function ({self.eval_avg})')
         if x.dim() == 2 and x.shape[0] == 0:
+            # an empty shard still joins the collective of its group (the other ranks would block in it otherwise)
+            if self.process_group is not None:
+                if not x.is_cuda:
+                    raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback)")
+                return self._finish(torch.empty((0, 64, 1), dtype=torch.float32, device=x.device), self._new_words(x.device))
             return torch.empty((0, self.outputdim), dtype=torch.float32, device=x.device)
-        db, max_pow = self.front_end.logmel_unclamped(x)
-        if self.process_group is not None:
-            # Q2: the top-dB cutoff is batch-global; with the batch sharded over GPUs the scope is the global batch.
-            torch.distributed.all_reduce(max_pow, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
-        return self.encode(db, max_pow)
+        if not x.is_cuda:
+            raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
+        words = self._new_words(x.device)
+        db, _ = self.front_end.logmel_unclamped(x, max_pow=words[0:1], min_pow=words[1:2])
+        return self._finish(db, words)
 
 
 def _forward_sliding(self, stream: torch.Tensor, hop: int = 1600, window: int = 16000) -> torch.Tensor:
@@ -434,20 +566,42 @@ def _forward_sliding(self, stream: torch.Tensor, hop: int = 1600, window: int = 
     windows, Q2), with the stream's STFT shared between overlapping windows (``FrontEnd.logmel_sliding``)."""
     if self.training:
         raise NotImplementedError("uit_mobile_b200 implements inference only: call model.eval()")
-    db, max_pow = self.front_end.logmel_sliding(stream, window, hop)
-    if self.process_group is not None:
-        torch.distributed.all_reduce(max_pow, op=torch.distributed.ReduceOp.MAX, group=self.process_group)
-    return self.encode(db, max_pow)
+    if not stream.is_cuda:
+        raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback)")
+    words = self._new_words(stream.device)
+    db, _ = self.front_end.logmel_sliding(stream, window, hop, max_pow=words[0:1], min_pow=words[1:2])
+    return self._finish(db, words)
 
 
 UITBase.forward_sliding = _forward_sliding
 
 
-def _factory(depth: int, kwargs) -> UITBase:
+def _factory(depth: int, kwargs, **fixed) -> UITBase:
     model_kwargs = dict(patch_size=16, embed_dim=128, depth=depth, num_heads=2, mlp_ratio=3.0, pooling='mean',
-                        init_bn=True, drop_path_rate=0.0, act_layer=nn.ReLU, attention_type='BNeckAttention')
+                        init_bn=True, drop_path_rate=0.0, **(fixed or dict(act_layer=nn.ReLU, attention_type='BNeckAttention')))
     model_kwargs = {**model_kwargs, **kwargs}
     return UITBase(**model_kwargs)
+
+
+# The reference's other h128 factories (uit.py:496-578): full Attention, GELU unless "_relu".  They run on the fp32 CUDA-core kernels.
+def audio_transformer_h128_d4_m3_relu(**kwargs):     # uit.py:513-528
+    return _factory(4, kwargs, act_layer=nn.ReLU)
+
+
+def audio_transformer_h128_d4_m3(**kwargs):          # uit.py:531-545
+    return _factory(4, kwargs, act_layer=None)
+
+
+def audio_transformer_h128_d6_m3(**kwargs):          # uit.py:547-561
+    return _factory(6, kwargs, act_layer=None)
+
+
+def audio_transformer_h128_d6_m3_relu(**kwargs):     # uit.py:563-578
+    return _factory(6, kwargs, act_layer=nn.ReLU)
+
+
+def audio_transformer_h128_d3_m3_bneck_v2_relu(**kwargs):   # uit.py:496-511: names a class the reference never defines (Q10)
+    return _factory(3, kwargs, act_layer=nn.ReLU, attention_type='BNeckAttentionV2')      # -> KeyError, as upstream
 
 
 def uit_xs(**kwargs):       # uit.py:581-597
