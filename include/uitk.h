@@ -117,8 +117,10 @@ UITK_API int uitk_logmel_sliding(const float* d_stream, int64_t n_samples, int64
                         float* d_db, uint32_t* d_max_pow, uint32_t* d_min_pow, void* d_workspace, size_t workspace_bytes,
                         void* stream);
 
-/* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120). */
-UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream);
+/* In-place top-dB clamp: db = max(db, 10*log10(max(max_pow,1e-10)) - top_db)  (amplitude_to_DB top_db=120).
+ * d_min_pow (may be NULL): the batch's minimum power word from uitk_logmel; when given, the kernel decides on the device
+ * whether any value lies under the cutoff and returns without touching memory if none does. */
+UITK_API int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, const uint32_t* d_min_pow, float top_db, void* stream);
 
 /* ---- encoder weights ----------------------------------------------------------------------------------------
  * Packs state_dict tensors (host fp32, reference layout) into the kernels' device layout.

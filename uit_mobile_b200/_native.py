@@ -55,7 +55,7 @@ SIGNATURES = {
     "uitk_logmel_sliding_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "uitk_logmel_sliding": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
-    "uitk_clamp_db": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p]),
+    "uitk_clamp_db": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "uitk_encoder_num_tensors": (C.c_int, [C.c_int]),
     "uitk_encoder_tensor_name": (C.c_char_p, [C.c_int, C.c_int]),
     "uitk_encoder_blob_bytes": (C.c_size_t, [C.POINTER(EncoderCfg)]),

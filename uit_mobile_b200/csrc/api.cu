@@ -98,12 +98,12 @@ int uitk_logmel_sliding(const float* d_stream, int64_t n_samples, int64_t window
   return launch_logmel_frames(d_stream, W, window, hop, blob, d_db, Tw - 2, 2, 64 * Tw, Tw, d_max_pow, d_min_pow, s);
 }
 
-int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, float top_db, void* stream) {
+int uitk_clamp_db(float* d_db, int64_t n, const uint32_t* d_max_pow, const uint32_t* d_min_pow, float top_db, void* stream) {
   UITK_REQUIRE(d_db && d_max_pow, UITK_EINVAL, "null pointer");
   UITK_REQUIRE(n >= 0, UITK_EINVAL, "negative size");
   int rc = check_arch();
   if (rc != UITK_OK) return rc;
-  return launch_clamp_db(d_db, n, d_max_pow, top_db, reinterpret_cast<cudaStream_t>(stream));
+  return launch_clamp_db(d_db, n, d_max_pow, d_min_pow, top_db, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static int encoder_geometry(const uitk_encoder_cfg* cfg, int64_t B, int64_t T, int target_length, int64_t* rows) {

@@ -331,8 +331,11 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   }
 }
 
-__global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint32_t* __restrict__ max_pow, float top_db) {
+__global__ void clamp_db_kernel(float* __restrict__ db, long long n, const uint32_t* __restrict__ max_pow,
+                                const uint32_t* __restrict__ min_pow, float top_db) {
   const float cutoff = 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*max_pow), 1e-10f)) - top_db;   // same map as the kernel
+  // the smallest dB value of the batch is this map of the minimum power word: nothing to clamp -> nothing to read or write
+  if (min_pow != nullptr && 3.01029995663981195f * __log2f(fmaxf(__uint_as_float(*min_pow), 1e-10f)) >= cutoff) return;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) db[i] = fmaxf(db[i], cutoff);
 }
@@ -412,11 +415,11 @@ int launch_logmel_i16(const int16_t* pcm, int64_t B, int64_t L, int64_t ld, cons
   return launch_logmel_t<int16_t>(pcm, B, L, ld, blob, db, max_pow, min_pow, s);
 }
 
-int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, float top_db, cudaStream_t s) {
+int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, const uint32_t* min_pow, float top_db, cudaStream_t s) {
   if (n == 0) return UITK_OK;
   int blocks = (int)((n + 1023) / 1024);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  clamp_db_kernel<<<blocks, 256, 0, s>>>(db, (long long)n, max_pow, top_db);
+  clamp_db_kernel<<<blocks, 256, 0, s>>>(db, (long long)n, max_pow, min_pow, top_db);
   count_launches(1);
   UITK_CHECK_CUDA(cudaGetLastError());
   return UITK_OK;

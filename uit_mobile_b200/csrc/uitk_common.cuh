@@ -110,7 +110,7 @@ int launch_logmel_i16(const int16_t* pcm, int64_t B, int64_t L, int64_t ld, cons
 int launch_logmel_frames(const float* wav, int64_t B, int64_t L, int64_t ld, const FrontendBlob* blob, float* db, int64_t t0, int64_t tn,
                          int64_t out_bs, int64_t out_ms, uint32_t* max_pow, uint32_t* min_pow, cudaStream_t s);
 int launch_window_gather(const float* G, int64_t U, float* dbw, int64_t W, int Tw, int r, cudaStream_t s);
-int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, float top_db, cudaStream_t s);
+int launch_clamp_db(float* db, int64_t n, const uint32_t* max_pow, const uint32_t* min_pow, float top_db, cudaStream_t s);
 
 struct EncoderArgs {
   const uitk_encoder_cfg* cfg;

@@ -185,11 +185,27 @@ class FrontEnd(nn.Sequential):
     """``front_end`` of the reference (uit.py:298-308): log-mel in dB with the batch-global top-dB clamp,
     [B, L] -> [B, 64, T], computed by the fused CUDA kernel."""
 
+    def new_words(self, device) -> torch.Tensor:
+        device = torch.device(device)
+        cache = self.__dict__.setdefault("_words_init", {})
+        if device not in cache:
+            cache[device] = torch.tensor([0, 0x7F800000], dtype=torch.int32, device=device)
+        return cache[device].clone()
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        db, max_pow = self.logmel_unclamped(x)
-        n = db.numel()
-        N.check(N.lib().uitk_clamp_db(db.data_ptr(), n, max_pow.data_ptr(), float(self[1].top_db),
-                                      torch.cuda.current_stream(db.device).cuda_stream), "uitk_clamp_db")
+        if not x.is_cuda:
+            raise N.UitkError("UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
+        words = self.new_words(x.device)                                                # [max power bits, min power bits]
+        db, _ = self.logmel_unclamped(x, max_pow=words[0:1], min_pow=words[1:2])
+        return self.clamp_(db, words[0:1], words[1:2])
+
+    def clamp_(self, db: torch.Tensor, max_pow: torch.Tensor, min_pow: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """In-place top-dB clamp (AmplitudeToDB(top_db=120), one cutoff for the whole batch: Q2).  With the batch's minimum
+        power word the pass decides on the device whether any value lies under the cutoff and returns at once if none does
+        (true for any realistic signal: the 4 bytes/value read-modify-write pass is then free)."""
+        with torch.cuda.device(db.device):
+            N.check(N.lib().uitk_clamp_db(db.data_ptr(), db.numel(), max_pow.data_ptr(), None if min_pow is None else min_pow.data_ptr(),
+                                          float(self[1].top_db), torch.cuda.current_stream(db.device).cuda_stream), "uitk_clamp_db")
         return db
 
     def _blob(self, device: torch.device) -> torch.Tensor:
@@ -539,7 +555,9 @@ class UITBase(nn.Module):
         return probs
 
     def _new_words(self, device) -> torch.Tensor:
-        return torch.tensor([0, 0x7F800000], dtype=torch.int32, device=device)       # [max power bits, min power bits (+inf)]
+        """[max power bits = 0, min power bits = +inf] on ``device``: a device-side clone of a cached constant (building the
+        tensor from a Python list would be a blocking pageable host-to-device copy in every forward)."""
+        return self.front_end.new_words(device)
 
     def forward(self, x: torch.Tensor, mixup=None) -> torch.Tensor:
         if self.training:

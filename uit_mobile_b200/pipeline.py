@@ -77,7 +77,10 @@ class HostPipeline:
         max_w, min_w = self.words[0:1], self.words[1:2]
         self.copy_stream.wait_stream(main)
         sharded = m.process_group is not None
-        spec = self.speculative and not sharded       # sharded: the scope is the global batch -> encode after the all-reduce
+        # Sharded: the top-dB scope is the GLOBAL batch.  Speculation stays on (tensor-core configuration): every chunk is encoded
+        # with this rank's running maximum, ONE all-reduce(MAX) of the word follows the last chunk, and the host check below
+        # compares this rank's minimum with the global cutoff.
+        spec = self.speculative and (not sharded or m._cfg().tensor_core)
         free = [None, None]                           # compute-done events per staging buffer
         for i, b0 in enumerate(range(0, B, self.chunk)):
             nb = min(self.chunk, B - b0)
@@ -101,24 +104,98 @@ class HostPipeline:
                 with torch.cuda.stream(self.d2h_stream):
                     self.d2h_stream.wait_event(scored)
                     self.out_host[b0:b0 + nb].copy_(self.probs[b0:b0 + nb], non_blocking=True)
+        final = self.words                             # [final max, this rank's min]
         if sharded:
-            torch.distributed.all_reduce(max_w, op=torch.distributed.ReduceOp.MAX, group=m.process_group)
+            final = self.words.clone()
+            torch.distributed.all_reduce(final[0:1], op=torch.distributed.ReduceOp.MAX, group=m.process_group)
         if not spec:
-            m.encode(self.db[:B], max_w, out=self.probs[:B])
+            m.encode(self.db[:B], final[0:1], out=self.probs[:B])
         out = self.out_host[:B]
         if not spec:
             out.copy_(self.probs[:B], non_blocking=True)
-        self.words_host.copy_(self.words, non_blocking=True)
+        self.words_host.copy_(final, non_blocking=True)
         main.synchronize()
         self.d2h_stream.synchronize()
         if spec:
             mx, mn = int(self.words_host[0]), int(self.words_host[1])
-            if _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:      # conservative margin vs the device's log2-based dB
+            if B and _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:      # conservative margin vs the device's log2-based dB
                 # some value lies below the final cutoff: redo the encoder with the final batch maximum (exact path)
                 self.respeculated += 1
-                m.encode(self.db[:B], max_w, out=self.probs[:B])
+                m.encode(self.db[:B], final[0:1], out=self.probs[:B])
                 out.copy_(self.probs[:B], non_blocking=True)
                 main.synchronize()
         self.h2d_bytes = B * self.L * wav_host.element_size()
         self.d2h_bytes = B * m.outputdim * 4 + 8
         return out
+
+
+class FrontEndHostPipeline:
+    """``model.front_end`` for host buffers (BASELINE config 4: the log-mel front-end alone): pinned host waveforms [B, L] in,
+    pinned host log-mel dB [B, 64, T] out.  Chunked like ``HostPipeline``: the H2D copy of chunk i+1 overlaps the log-mel kernel
+    of chunk i, and the UN-clamped dB of every chunk goes back at once on a third stream.  The reference's top-dB clamp is
+    batch-global (Q2); the kernels track the batch minimum, and ``min_dB >= max_dB - 120`` proves that the clamp would not have
+    changed a single value.  Otherwise the clamp pass runs on the device and the result is copied again (exact either way)."""
+
+    def __init__(self, model, max_batch: int, L: int, chunk: int = 256, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise N.UitkError("FrontEndHostPipeline needs the model on a CUDA device (no CPU fallback)")
+        if model.process_group is not None:
+            raise NotImplementedError("FrontEndHostPipeline is per rank; shard the clips and all-reduce the words yourself")
+        self.max_batch, self.L, self.chunk = max_batch, L, max(1, min(chunk, max_batch))
+        T = int(N.lib().uitk_num_frames(L))
+        dev = self.device
+        self.stage = [torch.empty((self.chunk, L), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.db = torch.empty((max_batch, 64, T), dtype=torch.float32, device=dev)
+        self.out_host = torch.empty((max_batch, 64, T), dtype=torch.float32).pin_memory()
+        self.words = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.words_init = torch.tensor([0, _INF_BITS], dtype=torch.int32, device=dev)
+        self.words_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.copy_stream, self.d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.reclamped = 0
+
+    @torch.no_grad()
+    def __call__(self, wav_host: torch.Tensor) -> torch.Tensor:
+        if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 2 or wav_host.shape[1] != self.L:
+            raise ValueError(f"expected a host float32 [B, {self.L}] tensor")
+        B = wav_host.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds the pipeline capacity {self.max_batch}")
+        fe = self.model.front_end
+        main = torch.cuda.current_stream(self.device)
+        self.words.copy_(self.words_init)
+        max_w, min_w = self.words[0:1], self.words[1:2]
+        self.copy_stream.wait_stream(main)
+        self.d2h_stream.wait_stream(main)
+        free = [None, None]
+        for i, b0 in enumerate(range(0, B, self.chunk)):
+            nb = min(self.chunk, B - b0)
+            buf = self.stage[i & 1][:nb]
+            with torch.cuda.stream(self.copy_stream):
+                if free[i & 1] is not None:
+                    self.copy_stream.wait_event(free[i & 1])
+                buf.copy_(wav_host[b0:b0 + nb], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+            main.wait_event(ready)
+            fe.logmel_unclamped(buf, out=self.db[b0:b0 + nb], max_pow=max_w, min_pow=min_w)
+            done = torch.cuda.Event()
+            done.record(main)
+            free[i & 1] = done
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(done)
+                self.out_host[b0:b0 + nb].copy_(self.db[b0:b0 + nb], non_blocking=True)
+        self.words_host.copy_(self.words, non_blocking=True)
+        main.synchronize()
+        self.d2h_stream.synchronize()
+        mx, mn = int(self.words_host[0]), int(self.words_host[1])
+        if B and _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:
+            self.reclamped += 1
+            fe.clamp_(self.db[:B], max_w)
+            self.out_host[:B].copy_(self.db[:B], non_blocking=True)
+            main.synchronize()
+        self.h2d_bytes = B * self.L * 4
+        self.d2h_bytes = self.out_host[:B].numel() * 4 + 8
+        return self.out_host[:B]
