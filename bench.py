@@ -371,9 +371,11 @@ def run_b200(args):
     e0, e1 = ev(), ev()
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(steps):
         marks[i][0].record()
         probs = step(marks[i])
+    host_issue_ms = 1e3 * (time.perf_counter() - t_host0) / steps      # CPU time to ISSUE a step (launch-bound if >= ms_per_step)
     drain()                 # the last all-gather completes inside the timed region
     e1.record()
     barrier()
@@ -475,7 +477,7 @@ def run_b200(args):
                 "h2d_floor_gbs_per_gpu": h2d_floor,
                 "h2d_floor_note": f"bare pinned-host->device copy, all {world} rank(s) at once; the e2e step moves "
                                   f"{pipe.h2d_bytes / 1e6:.0f} MB in = {pipe.h2d_bytes / 1e6 / max(h2d_floor, 1e-9):.2f} ms at that rate"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms,
     }
     if e2e16:
         line["e2e_int16_pcm"] = e2e16

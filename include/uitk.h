@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 200
+#define UITK_VERSION 210
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.uitk_version() == 200
+    assert lib.uitk_version() == 210
 
 
 def test_geometry_helpers_match_oracle(lib):
@@ -46,22 +46,30 @@ def test_frontend_pack_layout(lib):
     blob = np.zeros(n, np.uint8)
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, n) == 0
     i32, f32 = blob.view(np.int32), blob.view(np.float32)
-    assert i32[0] == 0x55464531
+    assert i32[0] == 0x55464532
     np.testing.assert_array_equal(f32[4:516], win.numpy())
     tw256 = f32[516:516 + 512].reshape(256, 2)
     j = np.arange(256)
     np.testing.assert_allclose(tw256[:, 0] + 1j * tw256[:, 1], np.exp(-2j * np.pi * ((j >> 4) * (j & 15)) / 256), atol=1e-7)
     base = 516 + 1024
-    lo, iters, qoff = i32[base:base + 64], i32[base + 64:base + 68], i32[base + 68:base + 72]
-    w = f32[base + 80:]
-    assert (lo % 4 == 0).all() and i32[1] == 64 * iters.sum()
-    dense = np.zeros((257 + 64, 64), np.float32)
-    for m in range(64):
-        q, j = divmod(m, 16)
-        for i in range(iters[q]):
-            dense[lo[m] + 4 * i: lo[m] + 4 * i + 4, m] = w[qoff[q] + (i * 16 + j) * 4: qoff[q] + (i * 16 + j) * 4 + 4]
-    np.testing.assert_array_equal(dense[:257], 0.25 * fb.numpy())      # weights carry the 1/4 of the kernel's 4|X|^2
-    assert (dense[257:] == 0).all()
+    # tensor-core mel projection: per (mel octet, 8-bin group) block the mma.m16n8k8 B fragment, tf32 hi + lo
+    glo, gcnt, boff = i32[base:base + 8], i32[base + 8:base + 16], i32[base + 16:base + 24]
+    frag = f32[base + 32:].reshape(-1, 32, 4)
+    assert i32[1] == gcnt.sum() == frag.shape[0] and (boff == np.concatenate(([0], np.cumsum(gcnt)[:-1]))).all()
+    dense = np.zeros((8 * 33, 64), np.float64)
+    for o in range(8):
+        for u in range(gcnt[o]):
+            for lane in range(32):
+                tig, gid = lane & 3, lane >> 2
+                h0, h1, l0, l1 = frag[boff[o] + u, lane]
+                for v in (h0, h1, l0, l1):          # tf32 operands: low 13 mantissa bits clear
+                    assert np.float32(v).view(np.uint32) & 0x1fff == 0
+                k0 = 8 * (glo[o] + u) + 2 * tig
+                dense[k0, 8 * o + gid] = float(h0) + float(l0)
+                dense[k0 + 1, 8 * o + gid] = float(h1) + float(l1)
+    want = 0.25 * fb.numpy().astype(np.float64)                      # weights carry the 1/4 of the kernel's 4|X|^2
+    np.testing.assert_allclose(dense[:257], want, rtol=2.0 ** -21, atol=0)
+    assert (dense[257:] == 0).all() and frag.shape[0] <= 48          # HTK/64: 40 blocks of the 264 possible
     # error path: blob too small
     assert lib.uitk_pack_frontend(win.data_ptr(), fb.data_ptr(), blob.ctypes.data, 16) == -5
     assert b"needs" in lib.uitk_last_error()

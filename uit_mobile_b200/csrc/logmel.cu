@@ -27,8 +27,8 @@ constexpr int kSamplesPerRound = UITK_HOP * (kFramesPerRound - 1) + UITK_N_FFT; 
 // where the first clip's last frame ends, i.e. every slot of the second clip is shifted by n_fft - hop = 352 samples.
 constexpr int kStraddleShift = UITK_N_FFT - UITK_HOP;                            // 352
 constexpr int kStageFloats = kSamplesPerRound + kStraddleShift;                  // 3264
-constexpr int kExStride = 280;   // float2 per frame group: 16 x 17 used; 560 words = 16 mod 32 so that the two
-                                 // frame groups of a warp use complementary banks for 32-bit accesses
+constexpr int kExStride = 288;   // float2 per frame group: 16 x 17 used by the transpose; 576 words = 0 mod 32 (the power rows
+                                 // that reuse the tile are XOR-swizzled per frame slot instead)
 
 // cos / sin (2 pi m / 32), m = 0..15
 __device__ constexpr float kCos32[16] = {1.f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
@@ -87,12 +87,10 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 struct SmemLayout {
   float window[512];
-  int mel_lo[64], mel_iters[4], mel_qoff[4];
-  float x[2][kStageFloats];          // double buffered: cp.async stages round r+1 while round r computes
-  float2 ex[kFramesPerRound * kExStride];
-  float out[64 * 17];
+  float x[2][kStageFloats];          // double buffered: bulk copies stage round r+1 while round r computes
+  float2 ex[kFramesPerRound * kExStride];   // per frame group: 16x17 transpose tile, then the frame's 257 powers (swizzled)
   float red[16];
-  // followed by mel_w[n_weights]
+  uint64_t full[2];                  // mbarriers: "x[buf] landed"
 };
 
 // TIn = float (the reference's input contract) or int16_t (PCM ingest: x = pcm / 32768, dataset.py:44-46 /
@@ -135,6 +133,14 @@ __device__ __forceinline__ Round round_at(RoundPos P, int T, long long B, int st
   return R;
 }
 
+// D(16x8, fp32) += A(16x8, tf32, row) * B(8x8, tf32, col).  Fragments (lane = 4 * gid + tig): a0 = A[gid][tig], a1 = A[gid+8][tig],
+// a2 = A[gid][tig+4], a3 = A[gid+8][tig+4]; b0 = B[tig][gid], b1 = B[tig+4][gid]; d0/d1 = D[gid][2 tig, +1], d2/d3 = D[gid+8][..].
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 3)
 logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, int t0, long long out_bs, long long out_ms,
@@ -145,7 +151,6 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   // to db[clip * out_bs + mel * out_ms + t].
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
-  float* s_melw = reinterpret_cast<float*>(smem_raw + sizeof(SmemLayout));
 
   const int tid = threadIdx.x;
   const int g = tid >> 4;      // frame slot in the round
@@ -155,12 +160,14 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   const long long r_end = r_begin + rpc < num_rounds ? r_begin + rpc : num_rounds;
 
   constexpr bool kPcm = sizeof(TIn) == 2;
-  constexpr int kVec = 16 / (int)sizeof(TIn);          // samples per 16-byte cp.async
+  constexpr int kVec = 16 / (int)sizeof(TIn);          // samples per 16 bytes
+  if (tid == 0) {
+    tc::mbar_init(&S.full[0], 1);
+    tc::mbar_init(&S.full[1], 1);
+    tc::fence_barrier_init();
+  }
   for (int i = tid; i < 512; i += kThreads) S.window[i] = kPcm ? blob->window[i] * (1.f / 32768.f) : blob->window[i];
-  if (tid < 64) S.mel_lo[tid] = blob->mel_lo[tid];
-  if (tid < 4) { S.mel_iters[tid] = blob->mel_iters[tid]; S.mel_qoff[tid] = blob->mel_qoff[tid]; }
-  const int nw = blob->n_weights;
-  for (int i = tid; i < nw; i += kThreads) s_melw[i] = blob->mel_w[i];
+  __syncthreads();
 
   float tmax = 0.f, tmin = INFINITY;
   // thread-constant twiddles kept in registers: W256^(j*2^i) (the other powers are products of these) and W512^j
@@ -168,53 +175,77 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   const float2 wj512 = blob->tw512[j];
   const int Li = (int)L;
 
-  // Stage the samples of round r into S.x[buf]: 16-byte cp.async for groups that lie inside their clip (and are 16-B
-  // aligned), synchronous loads with the reflect index map (no edge repeat) for the few groups at the clip edges.
+  // Stage the samples of round r into S.x[buf] (warp 0 only).  A round reads one sample range per clip it touches (two when it
+  // straddles a clip boundary); the part of a range that lies inside its clip is ONE 1-D bulk copy (cp.async.bulk, completion
+  // on S.full[buf]) issued by lane 0, the few samples of the reflect padding at the clip edges (and everything, if the clip's
+  // rows are not 16-byte aligned) are written by the warp's lanes with the reflect index map (no edge repeat).
   auto stage = [&](long long r, RoundPos P, int buf) {
-    if (r < r_end) {
-      const Round R = round_at(P, T, B, straddle);
-      const int lenA = UITK_HOP * (R.nA - 1) + UITK_N_FFT;                       // floats of clip cA's range
-      const int total = R.nB > 0 ? lenA + UITK_HOP * (R.nB - 1) + UITK_N_FFT : lenA;
-      const TIn* clipA = wav + R.cA * ld;
-      const TIn* clipB = clipA + ld;
-      const bool okA = (reinterpret_cast<uintptr_t>(clipA) & 15) == 0, okB = (reinterpret_cast<uintptr_t>(clipB) & 15) == 0;
-      const int s0A = (t0 + R.tA) * UITK_HOP - UITK_N_FFT / 2;
-      const int s0B = t0 * UITK_HOP - UITK_N_FFT / 2;
-      TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
-      for (int i = tid * kVec; i < total; i += kThreads * kVec) {
-        const bool inA = i < lenA;                           // lenA is a multiple of kVec: a group never spans both clips
-        const TIn* clip = inA ? clipA : clipB;
-        const int idx = inA ? s0A + i : s0B + (i - lenA);
-        if ((inA ? okA : okB) && idx >= 0 && idx + kVec - 1 < Li) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(clip + idx)
-                       : "memory");
-        } else {
+    if (r >= r_end || tid >= 32) return;
+    const Round R = round_at(P, T, B, straddle);
+    TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
+    const int lenA = UITK_HOP * (R.nA - 1) + UITK_N_FFT;
+    int len[2], s0[2], lo[2], hi[2];
+    len[0] = lenA; len[1] = R.nB > 0 ? UITK_HOP * (R.nB - 1) + UITK_N_FFT : 0;
+    s0[0] = (t0 + R.tA) * UITK_HOP - UITK_N_FFT / 2; s0[1] = t0 * UITK_HOP - UITK_N_FFT / 2;
+    uint32_t tx = 0;
 #pragma unroll
-          for (int e = 0; e < kVec; ++e) {
-            int id = idx + e;
-            if (id < 0) id = -id;
-            if (id >= Li) id = 2 * (Li - 1) - id;
-            dst[i + e] = (id >= 0 && id < Li) ? __ldg(clip + id) : TIn(0);
-          }
-        }
+    for (int p = 0; p < 2; ++p) {
+      const TIn* clip = wav + (R.cA + p) * ld;
+      lo[p] = max(0, -s0[p]);                                 // s0 is a multiple of 32 samples: lo keeps the 16-byte alignment
+      hi[p] = min(len[p], Li - s0[p]);
+      hi[p] = lo[p] + ((hi[p] - lo[p]) & ~(kVec - 1));
+      if (hi[p] < lo[p] || (reinterpret_cast<uintptr_t>(clip) & 15) != 0) lo[p] = hi[p] = 0;
+      tx += (uint32_t)(hi[p] - lo[p]) * (uint32_t)sizeof(TIn);
+    }
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&S.full[buf], tx);
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+        if (hi[p] > lo[p])
+          tc::bulk_g2s(dst + (p ? lenA : 0) + lo[p], wav + (R.cA + p) * ld + s0[p] + lo[p], (uint32_t)(hi[p] - lo[p]) * (uint32_t)sizeof(TIn),
+                       &S.full[buf]);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (hi[p] - lo[p] == len[p]) continue;                  // the usual case: nothing left for the scalar path
+      const TIn* clip = wav + (R.cA + p) * ld;
+      TIn* d = dst + (p ? lenA : 0);
+      for (int i = tid; i < len[p] - (hi[p] - lo[p]); i += 32) {
+        const int ii = i < lo[p] ? i : i + (hi[p] - lo[p]);
+        int id = s0[p] + ii;
+        if (id < 0) id = -id;
+        if (id >= Li) id = 2 * (Li - 1) - id;
+        d[ii] = (id >= 0 && id < Li) ? __ldg(clip + id) : TIn(0);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   RoundPos pos = round_pos(r_begin, T, straddle, rounds_per_clip);
   stage(r_begin, pos, 0);
 
+  // mel phase: warp = mel octet, lane = 4 * gid + tig (mma fragment coordinates)
+  const int lane = tid & 31, oct = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  const int mel_glo = blob->mel_glo[oct], mel_gcnt = blob->mel_gcnt[oct];
+  const float4* frag = blob->mel_frag + (size_t)blob->mel_boff[oct] * 32 + lane;
+  // Power rows: the two frame slots 2p, 2p + 1 of warp p share one row, bin-interleaved, that reuses the warp's transpose tiles:
+  // P[2p + h][k] at float 2 * (k ^ swz(p)) + h.  A 16-byte load at bins (b, b + 1) is then exactly the A fragment of mma rows
+  // p / p + 8 (= slots 2p / 2p + 1) for logical k = tig / tig + 4 <-> bins b = 8G + 2 tig, b + 1; the stores of a warp's two frame
+  // groups hit even / odd banks; the XOR (8 bins for odd p) keeps the two rows of a quarter-warp load in different bank halves.
+  float* prow_w = reinterpret_cast<float*>(S.ex + (g & ~1) * kExStride) + (g & 1);
+  const int swz_w = (g & 2) << 2;
+  const float* prow_r = reinterpret_cast<const float*>(S.ex + 2 * gid * kExStride);
+  const int swz_r = (gid & 1) << 3;
+
   int buf = 0;
   for (long long r = r_begin; r < r_end; ++r, buf ^= 1) {
     const RoundPos pos_next = next_pos(pos, T, straddle);
-    stage(r + 1, pos_next, buf ^ 1);                   // buffer last read two barriers ago
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();   // S.x[buf] (and the constants) visible; previous round's S.out readers are done
+    stage(r + 1, pos_next, buf ^ 1);                   // buffer last read before the previous round's second barrier
+    tc::mbar_wait(&S.full[buf], (uint32_t)(((r - r_begin) >> 1) & 1));
+    __syncthreads();   // scalar-staged edge samples of S.x[buf] visible; previous round's power rows are consumed
     const TIn* sx = reinterpret_cast<const TIn*>(S.x[buf]);
     const Round R = round_at(pos, T, B, straddle);
     pos = pos_next;
-    const bool live = g < R.nA + R.nB;
-    const bool warp_live = (g & ~1) < R.nA + R.nB;     // warp-uniform: the warp's first frame group is live
+    const int n_live = R.nA + R.nB;
+    const bool warp_live = (g & ~1) < n_live;          // warp-uniform: the warp's first frame group is live
 
     if (warp_live) {
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
@@ -251,64 +282,63 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
     __syncwarp();
     fft16(v);                                   // over n1 -> k2 ; v[k2] = Z[j + 16 k2]
 
-    // ---- real-FFT unpack + power: X[k] = E[k] + W512^k O[k], k = j + 16 m.  The partner Z[256-k] lives in lane
-    // (16-j) of this frame group at register 15-m (lane 0: its own register (16-m)&15): one shuffle, static indices.
-    // W512^k = W512^j * W32^m with W32^m compile-time constants.
-    // 2 X[k] = (A + B) + G (A - B) with A = Z[k], B = conj(Z[256-k]), G = -i W512^k; G[m+1] = G[m] * W32 (<= 16 roundings).
-    // The factor 1/4 of |X|^2 is folded into the packed mel weights (exact: power of two).
-    float p[16];
-    float2 G = make_float2(wj512.y, -wj512.x);                     // -i * W512^j
+    // ---- real-FFT unpack + power, two bins per step.  With A = Z[k], B = conj(Z[256-k]), G = -i W512^k:
+    //   2 X[k] = (A + B) + G (A - B)        2 conj(X[256-k]) = (A + B) - G (A - B)
+    // so the thread that owns k = j + 16 m (m < 8) produces the powers of k AND of 256 - k from one partner value:
+    // Z[256-k] is register 15 - m of lane 16 - j of this frame group (lane 0: its own register (16 - m) & 15), fetched with ONE
+    // shuffle pair.  Lane 0 adds k = 128 (its own partner).  G = (-i W512^j) * W32^m with compile-time W32^m.  Powers are kept
+    // as 4 |X|^2; the factor 1/4 is folded into the mel weights (exact: power of two).
+    const float2 G0 = make_float2(wj512.y, -wj512.x);             // -i * W512^j
+    const int pl = (16 - j) & 15;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
+    for (int m = 0; m < 8; ++m) {
       const float2 zk = v[m];
+      float2 src = v[15 - m];
+      if (j == 0) src = v[(16 - m) & 15];
       float2 zn;
-      zn.x = __shfl_sync(0xffffffffu, v[15 - m].x, (16 - j) & 15, 16);
-      zn.y = __shfl_sync(0xffffffffu, v[15 - m].y, (16 - j) & 15, 16);
-      if (j == 0) zn = v[(16 - m) & 15];
+      zn.x = __shfl_sync(0xffffffffu, src.x, pl, 16);
+      zn.y = __shfl_sync(0xffffffffu, src.y, pl, 16);
       const float2 S2 = fma2(zn, make_float2(1.f, -1.f), zk);     // A + B
       const float2 D2 = fma2(zn, make_float2(-1.f, 1.f), zk);     // A - B
-      const float2 X2 = cadd(S2, cmul(D2, G));
-      p[m] = fmaf(X2.x, X2.x, X2.y * X2.y);                       // 4 |X[k]|^2
-      G = cmul(G, make_float2(kCos32[1], -kSin32[1]));
+      const float2 Gm = m == 0 ? G0 : cmul(G0, make_float2(kCos32[m], -kSin32[m]));
+      const float2 Tm = cmul(D2, Gm);
+      const float2 Xp = cadd(S2, Tm), Xn = csub(S2, Tm);
+      const int k = j + 16 * m;
+      prow_w[2 * (k ^ swz_w)] = fmaf(Xp.x, Xp.x, Xp.y * Xp.y);              // 4 |X[k]|^2
+      prow_w[2 * ((256 - k) ^ swz_w)] = fmaf(Xn.x, Xn.x, Xn.y * Xn.y);      // 4 |X[256-k]|^2
     }
-    __syncwarp();
-    float* pf = reinterpret_cast<float*>(e);
-#pragma unroll
-    for (int m = 0; m < 16; ++m) pf[j + 16 * m] = p[m];
-    if (j == 0) {
-      const float ny = 2.f * (v[0].x - v[0].y);   // X[256] = Re Z0 - Im Z0 (x2: powers are kept as 4 |X|^2)
-      pf[256] = ny * ny;
-    }
-    __syncwarp();
-
-    // ---- sparse mel + dB
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int m = j + 16 * q;
-      const int iters = S.mel_iters[q];
-      const float4* wq = reinterpret_cast<const float4*>(s_melw + S.mel_qoff[q]) + j;     // lane-interleaved weights
-      const float4* pq = reinterpret_cast<const float4*>(pf + S.mel_lo[m]);               // 4-aligned range start
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int i = 0; i < iters; ++i) {            // uniform trip count per group; short ranges carry zero weights
-        const float4 w4 = wq[i * 16];
-        const float4 p4 = pq[i];
-        a0 = fmaf(w4.x, p4.x, a0); a1 = fmaf(w4.y, p4.y, a1);
-        a2 = fmaf(w4.z, p4.z, a2); a3 = fmaf(w4.w, p4.w, a3);
-      }
-      const float acc = (a0 + a1) + (a2 + a3);
-      if (live) { tmax = fmaxf(tmax, acc); tmin = fminf(tmin, acc); }
-      S.out[m * 17 + g] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));   // 10 log10(x); |err| ~1e-6 dB
-    }
+    if (j == 0) prow_w[2 * (128 ^ swz_w)] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);   // X[128] = conj(Z[128])
     }   // warp_live
     __syncthreads();
-    {   // S.out [64 mel][16 slots] -> db: this thread stores slot gg = tid & 15 of mel rows (tid >> 4) + 16 it
-      const int gg = tid & 15;
-      if (gg < R.nA + R.nB) {
-        const bool inA = gg < R.nA;
-        float* o = db + (inA ? R.cA : R.cA + 1) * out_bs + (tid >> 4) * out_ms + t0 + (inA ? R.tA + gg : gg - R.nA);
-        const float* so = S.out + (tid >> 4) * 17 + gg;
+
+    // ---- mel projection on the tensor cores + dB.  D[16 frame slots][8 mel bins of this warp's octet] = P[16][8 bins] * W[8 bins][8]
+    // summed over the octet's bin groups; P and W as tf32 hi + lo, three products (hi*hi + lo*hi + hi*lo: ~2^-21 relative).
+    {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f}, acw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int u = 0; u < mel_gcnt; ++u) {
+        // (P[2 gid][b], P[2 gid + 1][b], P[2 gid][b + 1], P[2 gid + 1][b + 1]), b = 8 G + 2 tig  ==  (a0, a1, a2, a3)
+        const float4 pa = *reinterpret_cast<const float4*>(prow_r + 2 * ((8 * (mel_glo + u)) ^ swz_r) + 4 * tig);
+        const float4 wf = __ldg(frag + u * 32);
+        const uint32_t a0 = __float_as_uint(pa.x) & 0xffffe000u, a1 = __float_as_uint(pa.y) & 0xffffe000u;
+        const uint32_t a2 = __float_as_uint(pa.z) & 0xffffe000u, a3 = __float_as_uint(pa.w) & 0xffffe000u;
+        const uint32_t l0 = __float_as_uint(pa.x - __uint_as_float(a0)), l1 = __float_as_uint(pa.y - __uint_as_float(a1));
+        const uint32_t l2 = __float_as_uint(pa.z - __uint_as_float(a2)), l3 = __float_as_uint(pa.w - __uint_as_float(a3));
+        mma_tf32(acc, a0, a1, a2, a3, __float_as_uint(wf.x), __float_as_uint(wf.y));
+        mma_tf32(acl, l0, l1, l2, l3, __float_as_uint(wf.x), __float_as_uint(wf.y));
+        mma_tf32(acw, a0, a1, a2, a3, __float_as_uint(wf.z), __float_as_uint(wf.w));
+      }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) o[it * 16 * out_ms] = so[it * 16 * 17];
+      for (int h = 0; h < 2; ++h) {
+        const int s = 2 * gid + h;                   // mma rows gid / gid + 8 are frame slots 2 gid / 2 gid + 1
+        if (s < n_live) {
+          const bool inA = s < R.nA;
+          float* o = db + (inA ? R.cA : R.cA + 1) * out_bs + (long long)(8 * oct + 2 * tig) * out_ms + t0 + (inA ? R.tA + s : s - R.nA);
+          const float m0 = acc[2 * h] + (acl[2 * h] + acw[2 * h]), m1 = acc[2 * h + 1] + (acl[2 * h + 1] + acw[2 * h + 1]);
+          tmax = fmaxf(tmax, fmaxf(m0, m1)); tmin = fminf(tmin, fminf(m0, m1));
+          o[0] = 3.01029995663981195f * __log2f(fmaxf(m0, 1e-10f));          // 10 log10(x); |err| ~1e-6 dB
+          o[out_ms] = 3.01029995663981195f * __log2f(fmaxf(m1, 1e-10f));
+        }
       }
     }
   }
@@ -351,8 +381,8 @@ static int launch_logmel_t(const TIn* wav, int64_t B, int64_t L, int64_t ld, con
   if (out_ms < 0) out_ms = Tall;
   if (out_bs < 0) out_bs = 64 * Tall;
   if (T == 0 || B == 0) return UITK_OK;
-  const size_t smem = sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights;
-  static_assert(3 * (sizeof(SmemLayout) + sizeof(float) * kMaxMelWeights + 1024) <= 228 * 1024, "three CTAs per SM");
+  const size_t smem = sizeof(SmemLayout);
+  static_assert(3 * (sizeof(SmemLayout) + 1024) <= 228 * 1024, "three CTAs per SM");
   UITK_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // rounds of 16 consecutive frames of the flat frame list (T >= 16), else per-clip rounds
   const int straddle = T >= kFramesPerRound ? 1 : 0;

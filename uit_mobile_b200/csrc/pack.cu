@@ -132,14 +132,44 @@ int uitk_num_crops(int64_t T, int target_length) { return crops_for(T, target_le
 int uitk_tokens_per_crop(int64_t T, int target_length) { return 4 * time_patches_for(T, target_length); }
 int uitk_tokens_total(const uitk_encoder_cfg* cfg, int64_t T, int target_length) { return cfg ? tokens_total_for(*cfg, T, target_length) : 0; }
 
-size_t uitk_frontend_blob_bytes(const float* h_fb) { (void)h_fb; return sizeof(FrontendBlob); }
+// (octet, 8-bin group) blocks of the filterbank that hold a non-zero entry: first group / group count per octet
+static int mel_block_ranges(const float* h_fb, int* glo, int* gcnt) {
+  int n = 0;
+  for (int o = 0; o < kMelOctets; ++o) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < UITK_N_FREQS; ++k)
+      for (int m = 8 * o; m < 8 * o + 8; ++m)
+        if (h_fb[(size_t)k * UITK_N_MELS + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    glo[o] = lo < 0 ? 0 : lo / 8;
+    gcnt[o] = lo < 0 ? 0 : hi / 8 - lo / 8 + 1;
+    n += gcnt[o];
+  }
+  return n;
+}
+
+static float tf32_trunc(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u &= 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+size_t uitk_frontend_blob_bytes(const float* h_fb) {
+  int glo[kMelOctets], gcnt[kMelOctets];
+  return frontend_blob_bytes(h_fb ? mel_block_ranges(h_fb, glo, gcnt) : kMelOctets * kMelGroups);
+}
 
 int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, size_t blob_bytes) {
   UITK_REQUIRE(h_window && h_fb && h_blob, UITK_EINVAL, "null pointer");
-  UITK_REQUIRE(blob_bytes >= sizeof(FrontendBlob), UITK_ENOSPACE, "front-end blob needs %zu bytes", sizeof(FrontendBlob));
+  int glo[kMelOctets], gcnt[kMelOctets];
+  const int n_blocks = mel_block_ranges(h_fb, glo, gcnt);
+  const size_t need = frontend_blob_bytes(n_blocks);
+  UITK_REQUIRE(blob_bytes >= need, UITK_ENOSPACE, "front-end blob needs %zu bytes", need);
   FrontendBlob* fb = reinterpret_cast<FrontendBlob*>(h_blob);
-  memset(fb, 0, sizeof(FrontendBlob));
+  memset(fb, 0, need);
   fb->magic = kFrontendMagic;
+  fb->n_blocks = n_blocks;
   memcpy(fb->window, h_window, sizeof(float) * 512);
   const double two_pi = 6.283185307179586476925286766559;
   for (int j = 0; j < 256; ++j) {
@@ -149,37 +179,20 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
     fb->tw256[j] = make_float2((float)cos(two_pi * (ln * k1) / 256.0), (float)-sin(two_pi * (ln * k1) / 256.0));
     fb->tw512[j] = make_float2((float)cos(two_pi * j / 512.0), (float)-sin(two_pi * j / 512.0));
   }
-  int lo_[UITK_N_MELS], hi_[UITK_N_MELS];
-  for (int m = 0; m < UITK_N_MELS; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < UITK_N_FREQS; ++k)
-      if (h_fb[(size_t)k * UITK_N_MELS + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-    if (lo < 0) { lo = 0; hi = -1; }
-    lo_[m] = lo & ~3;                    // 4-aligned start: the kernel reads the power spectrum as float4
-    hi_[m] = hi;
-    fb->mel_lo[m] = lo_[m];
+  int b = 0;
+  for (int o = 0; o < kMelOctets; ++o) {
+    fb->mel_glo[o] = glo[o]; fb->mel_gcnt[o] = gcnt[o]; fb->mel_boff[o] = b;
+    for (int u = 0; u < gcnt[o]; ++u, ++b)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int tig = lane & 3, gid = lane >> 2, k0 = 8 * (glo[o] + u) + 2 * tig, m = 8 * o + gid;
+        float w[2];
+        for (int e = 0; e < 2; ++e)       // x 1/4: the kernel keeps the power spectrum as 4 |X|^2 (exact scaling)
+          w[e] = k0 + e < UITK_N_FREQS ? 0.25f * h_fb[(size_t)(k0 + e) * UITK_N_MELS + m] : 0.f;
+        // tf32 hi + lo split (11 + 11 significant bits; the tensor core ignores the low 13 bits of an operand)
+        const float h0 = tf32_trunc(w[0]), h1 = tf32_trunc(w[1]);
+        fb->mel_frag[(size_t)b * 32 + lane] = make_float4(h0, h1, tf32_trunc(w[0] - h0), tf32_trunc(w[1] - h1));
+      }
   }
-  int n = 0;
-  for (int q = 0; q < 4; ++q) {
-    int iters = 0;
-    for (int j = 0; j < 16; ++j) {
-      const int m = 16 * q + j, len = hi_[m] - lo_[m] + 1;
-      if ((len + 3) / 4 > iters) iters = (len + 3) / 4;
-    }
-    UITK_REQUIRE(n + iters * 64 <= kMaxMelWeights, UITK_EINVAL,
-                 "mel filterbank too dense for the kernel (%d packed weights max)", kMaxMelWeights);
-    fb->mel_iters[q] = iters;
-    fb->mel_qoff[q] = n;
-    for (int i = 0; i < iters; ++i)
-      for (int j = 0; j < 16; ++j)
-        for (int e = 0; e < 4; ++e) {
-          const int m = 16 * q + j, k = lo_[m] + 4 * i + e;
-          // x 1/4: the kernel keeps the power spectrum as 4 |X|^2 (exact scaling)
-          fb->mel_w[n + (i * 16 + j) * 4 + e] = (k <= hi_[m] && k < UITK_N_FREQS) ? 0.25f * h_fb[(size_t)k * UITK_N_MELS + m] : 0.f;
-        }
-    n += iters * 64;
-  }
-  fb->n_weights = n;
   return UITK_OK;
 }
 

@@ -1,6 +1,7 @@
 // Shared internals of libuitk (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -32,24 +33,29 @@ void count_launches(int n);   // process-wide counter behind uitk_kernel_launche
 // ---------------------------------------------------------------------------------------------------------
 // Front-end constant blob (device layout).  All fields 4 bytes; header first.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kMaxMelWeights = 1792;   // packed filterbank entries kept in shared memory (HTK/64: 1024 incl. padding)
+// Mel projection on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulate): the 64 mel bins are 8 octets (one per warp), the
+// 257 frequency bins are 33 groups of 8; octet o multiplies the groups [mel_glo[o], mel_glo[o] + mel_gcnt[o]) that hold its
+// non-zero filterbank entries.  For every (octet, group) the blob carries the B fragment of that 8x8 weight block, split
+// into tf32 hi + lo: entry [lane] = (b0_hi, b1_hi, b0_lo, b1_lo) with b0 = W[8g + 2*(lane%4)][8o + lane/4],
+// b1 = W[8g + 2*(lane%4) + 1][8o + lane/4], W = 0.25 * fb (the kernel keeps the power spectrum as 4 |X|^2).
+constexpr int kMelOctets = 8;
+constexpr int kMelGroups = 33;                 // ceil(257 / 8); group 32 holds the Nyquist bin alone
 
 struct FrontendBlob {
-  int magic;                 // 'UFE1'
-  int n_weights;             // packed filterbank entries
+  int magic;                 // 'UFE2'
+  int n_blocks;              // (octet, group) weight blocks that follow the fixed part
   int pad0, pad1;
   float window[512];         // front_end.0.spectrogram.window
   float2 tw256[256];         // [k1*16 + lane] = exp(-2*pi*i*lane*k1/256)
   float2 tw512[256];         // exp(-2*pi*i*k/512)
-  int mel_lo[64];            // first frequency bin of mel bin m's range, rounded down to a multiple of 4
-  int mel_iters[4];          // float4 steps for the mel bins {16q .. 16q+15} (max range of the group / 4)
-  int mel_qoff[4];           // float offset of group q's weights in mel_w
+  int mel_glo[kMelOctets];   // first 8-bin group of octet o
+  int mel_gcnt[kMelOctets];  // number of groups
+  int mel_boff[kMelOctets];  // index of the octet's first block in mel_frag
   int pad2[8];
-  // group q, step i, lane j (mel bin 16q+j): 4 weights for bins lo+4i .. lo+4i+3 at mel_w[qoff + (i*16 + j)*4]; the 16
-  // lanes of a frame group read 16 consecutive float4 (conflict-free), shorter ranges are zero padded
-  float mel_w[kMaxMelWeights];
+  float4 mel_frag[1];        // [n_blocks][32 lanes], variable length (>= 1)
 };
-constexpr int kFrontendMagic = 0x55464531;
+inline size_t frontend_blob_bytes(int n_blocks) { return offsetof(FrontendBlob, mel_frag) + sizeof(float4) * 32 * (size_t)(n_blocks > 0 ? n_blocks : 1); }
+constexpr int kFrontendMagic = 0x55464532;
 
 // ---------------------------------------------------------------------------------------------------------
 // Encoder blob (fp32 section).  Offsets in floats from the start of the fp32 section.
