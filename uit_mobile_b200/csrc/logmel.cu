@@ -89,6 +89,8 @@ struct SmemLayout {
   float window[512];
   float x[2][kStageFloats];          // double buffered: bulk copies stage round r+1 while round r computes
   float2 ex[kFramesPerRound * kExStride];   // per frame group: 16x17 transpose tile, then the frame's 257 powers (swizzled)
+  float4 part[kMelSlots][32];        // partial mel sums of a split octet: producer warp(s) -> owner warp
+  MelBlk blk[kMelOctets][kMelWarpBlocks + 1];
   float red[16];
   uint64_t full[2];                  // mbarriers: "x[buf] landed"
 };
@@ -141,6 +143,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// 10 log10(max(x, 1e-10)) = 3.0103 log2(.): the argument is a normal number, so the flush-to-zero form (no denormal rescue) is exact
+// to the same ~1e-6 dB as __log2f
+__device__ __forceinline__ float power_to_db(float x) {
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(x, 1e-10f)));
+  return 3.01029995663981195f * l;
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 3)
 logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, int t0, long long out_bs, long long out_ms,
@@ -167,6 +177,7 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
     tc::fence_barrier_init();
   }
   for (int i = tid; i < 512; i += kThreads) S.window[i] = kPcm ? blob->window[i] * (1.f / 32768.f) : blob->window[i];
+  for (int i = tid; i < kMelOctets * (kMelWarpBlocks + 1); i += kThreads) (&S.blk[0][0])[i] = (&blob->mel_blk[0][0])[i];
   __syncthreads();
 
   float tmax = 0.f, tmin = INFINITY;
@@ -222,18 +233,20 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   RoundPos pos = round_pos(r_begin, T, straddle, rounds_per_clip);
   stage(r_begin, pos, 0);
 
-  // mel phase: warp = mel octet, lane = 4 * gid + tig (mma fragment coordinates)
-  const int lane = tid & 31, oct = tid >> 5, gid = lane >> 2, tig = lane & 3;
-  const int mel_glo = blob->mel_glo[oct], mel_gcnt = blob->mel_gcnt[oct];
-  const float4* frag = blob->mel_frag + (size_t)blob->mel_boff[oct] * 32 + lane;
+  // mel phase: lane = 4 * gid + tig (mma fragment coordinates); this warp's segments of the filterbank (uitk_common.cuh)
+  const int lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  const int mel_nblk = blob->mel_nblk[warp];
+  const float4* const frag0 = blob->mel_frag + lane;
+  const long long orow_tig = (long long)(2 * tig) * out_ms;
   // Power rows: the two frame slots 2p, 2p + 1 of warp p share one row, bin-interleaved, that reuses the warp's transpose tiles:
   // P[2p + h][k] at float 2 * (k ^ swz(p)) + h.  A 16-byte load at bins (b, b + 1) is then exactly the A fragment of mma rows
   // p / p + 8 (= slots 2p / 2p + 1) for logical k = tig / tig + 4 <-> bins b = 8G + 2 tig, b + 1; the stores of a warp's two frame
   // groups hit even / odd banks; the XOR (8 bins for odd p) keeps the two rows of a quarter-warp load in different bank halves.
+  // k = j + 16 m  ->  (j ^ swz) + 16 m;  256 - k = (16 - j) + 16 (15 - m)  ->  ((16 - j) ^ swz) + 16 (15 - m)   (swz = 0 | 8, also for j = 0)
   float* prow_w = reinterpret_cast<float*>(S.ex + (g & ~1) * kExStride) + (g & 1);
-  const int swz_w = (g & 2) << 2;
-  const float* prow_r = reinterpret_cast<const float*>(S.ex + 2 * gid * kExStride);
-  const int swz_r = (gid & 1) << 3;
+  float* const pk_base = prow_w + 2 * (j ^ ((g & 2) << 2));
+  float* const pn_base = prow_w + 2 * ((16 - j) ^ ((g & 2) << 2));
+  const float* const prow_r = reinterpret_cast<const float*>(S.ex + 2 * gid * kExStride) + 4 * tig;   // group G at + 16 * (G ^ (gid & 1))
 
   int buf = 0;
   for (long long r = r_begin; r < r_end; ++r, buf ^= 1) {
@@ -303,23 +316,34 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
       const float2 Gm = m == 0 ? G0 : cmul(G0, make_float2(kCos32[m], -kSin32[m]));
       const float2 Tm = cmul(D2, Gm);
       const float2 Xp = cadd(S2, Tm), Xn = csub(S2, Tm);
-      const int k = j + 16 * m;
-      prow_w[2 * (k ^ swz_w)] = fmaf(Xp.x, Xp.x, Xp.y * Xp.y);              // 4 |X[k]|^2
-      prow_w[2 * ((256 - k) ^ swz_w)] = fmaf(Xn.x, Xn.x, Xn.y * Xn.y);      // 4 |X[256-k]|^2
+      pk_base[32 * m] = fmaf(Xp.x, Xp.x, Xp.y * Xp.y);                      // 4 |X[k]|^2,       k = j + 16 m
+      pn_base[32 * (15 - m)] = fmaf(Xn.x, Xn.x, Xn.y * Xn.y);               // 4 |X[256-k]|^2
     }
-    if (j == 0) prow_w[2 * (128 ^ swz_w)] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);   // X[128] = conj(Z[128])
+    if (j == 0) pk_base[32 * 8] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);   // X[128] = conj(Z[128])
     }   // warp_live
     __syncthreads();
 
-    // ---- mel projection on the tensor cores + dB.  D[16 frame slots][8 mel bins of this warp's octet] = P[16][8 bins] * W[8 bins][8]
-    // summed over the octet's bin groups; P and W as tf32 hi + lo, three products (hi*hi + lo*hi + hi*lo: ~2^-21 relative).
+    // ---- mel projection on the tensor cores + dB.  D[16 frame slots][8 mel bins of an octet] = P[16][8 bins] * W[8 bins][8]
+    // summed over the segment's bin groups; P and W as tf32 hi + lo, three products (hi*hi + lo*hi + hi*lo: ~2^-21 relative).
+    // Every warp walks its list of weight blocks (uitk_common.cuh); a block with the fin bit ends a run of one octet.
     {
+      long long orow[2];                               // output offsets (mel 2 tig of octet 0) of this lane's two frame slots
+      const long long rowA = R.cA * out_bs + t0 + R.tA, rowB = (R.cA + 1) * out_bs + t0 - R.nA;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int s = 2 * gid + h;                     // mma rows gid / gid + 8 are frame slots 2 gid / 2 gid + 1
+        orow[h] = (s < R.nA ? rowA : rowB) + s + orow_tig;
+      }
+      const MelBlk* blk = S.blk[warp];
+      MelBlk me = blk[0];
+      float4 wf = __ldg(frag0 + (size_t)me.y * 32);
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f}, acw[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-      for (int u = 0; u < mel_gcnt; ++u) {
-        // (P[2 gid][b], P[2 gid + 1][b], P[2 gid][b + 1], P[2 gid + 1][b + 1]), b = 8 G + 2 tig  ==  (a0, a1, a2, a3)
-        const float4 pa = *reinterpret_cast<const float4*>(prow_r + 2 * ((8 * (mel_glo + u)) ^ swz_r) + 4 * tig);
-        const float4 wf = __ldg(frag + u * 32);
+#pragma unroll 1
+      for (int b = 0; b < mel_nblk; ++b) {
+        const MelBlk nx = blk[b + 1];
+        const float4 wn = __ldg(frag0 + (size_t)nx.y * 32);          // next block's weights under this block's math
+        // (P[2 gid][k], P[2 gid + 1][k], P[2 gid][k + 1], P[2 gid + 1][k + 1]), k = 8 G + 2 tig  ==  (a0, a1, a2, a3)
+        const float4 pa = *reinterpret_cast<const float4*>(prow_r + 16 * ((me.x & 0xff) ^ (gid & 1)));
         const uint32_t a0 = __float_as_uint(pa.x) & 0xffffe000u, a1 = __float_as_uint(pa.y) & 0xffffe000u;
         const uint32_t a2 = __float_as_uint(pa.z) & 0xffffe000u, a3 = __float_as_uint(pa.w) & 0xffffe000u;
         const uint32_t l0 = __float_as_uint(pa.x - __uint_as_float(a0)), l1 = __float_as_uint(pa.y - __uint_as_float(a1));
@@ -327,18 +351,37 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
         mma_tf32(acc, a0, a1, a2, a3, __float_as_uint(wf.x), __float_as_uint(wf.y));
         mma_tf32(acl, l0, l1, l2, l3, __float_as_uint(wf.x), __float_as_uint(wf.y));
         mma_tf32(acw, a0, a1, a2, a3, __float_as_uint(wf.z), __float_as_uint(wf.w));
-      }
+        if (me.x & 0x100) {                            // end of a run (warp-uniform)
+          const int role = (me.x >> 9) & 3, oct = (me.x >> 11) & 7, aux = me.x >> 14;
+          float m[4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int s = 2 * gid + h;                   // mma rows gid / gid + 8 are frame slots 2 gid / 2 gid + 1
-        if (s < n_live) {
-          const bool inA = s < R.nA;
-          float* o = db + (inA ? R.cA : R.cA + 1) * out_bs + (long long)(8 * oct + 2 * tig) * out_ms + t0 + (inA ? R.tA + s : s - R.nA);
-          const float m0 = acc[2 * h] + (acl[2 * h] + acw[2 * h]), m1 = acc[2 * h + 1] + (acl[2 * h + 1] + acw[2 * h + 1]);
-          tmax = fmaxf(tmax, fmaxf(m0, m1)); tmin = fminf(tmin, fminf(m0, m1));
-          o[0] = 3.01029995663981195f * __log2f(fmaxf(m0, 1e-10f));          // 10 log10(x); |err| ~1e-6 dB
-          o[out_ms] = 3.01029995663981195f * __log2f(fmaxf(m1, 1e-10f));
+          for (int i = 0; i < 4; ++i) { m[i] = acc[i] + (acl[i] + acw[i]); acc[i] = acl[i] = acw[i] = 0.f; }
+          if (role == kMelProducer) {                  // early part of a split octet: hand the partial sums to the owner
+            S.part[aux & 7][lane] = make_float4(m[0], m[1], m[2], m[3]);
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + oct), "r"(32 + 32 * (aux >> 3)) : "memory");
+          } else {
+            if (role == kMelOwner) {
+              asm volatile("bar.sync %0, %1;" ::"r"(1 + oct), "r"(32 + 32 * (aux & 3)) : "memory");
+              const float4 q = S.part[(aux >> 2) & 7][lane];
+              m[0] += q.x; m[1] += q.y; m[2] += q.z; m[3] += q.w;
+              if ((aux & 3) == 2) {
+                const float4 q2 = S.part[(aux >> 5) & 7][lane];
+                m[0] += q2.x; m[1] += q2.y; m[2] += q2.z; m[3] += q2.w;
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (2 * gid + h < n_live) {
+                float* o = db + orow[h] + (long long)(8 * oct) * out_ms;
+                const float m0 = m[2 * h], m1 = m[2 * h + 1];
+                tmax = fmaxf(tmax, fmaxf(m0, m1)); tmin = fminf(tmin, fminf(m0, m1));
+                o[0] = power_to_db(m0);
+                o[out_ms] = power_to_db(m1);
+              }
+            }
+          }
         }
+        me = nx; wf = wn;
       }
     }
   }

@@ -179,9 +179,10 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
     fb->tw256[j] = make_float2((float)cos(two_pi * (ln * k1) / 256.0), (float)-sin(two_pi * (ln * k1) / 256.0));
     fb->tw512[j] = make_float2((float)cos(two_pi * j / 512.0), (float)-sin(two_pi * j / 512.0));
   }
+  int boff[kMelOctets];
   int b = 0;
   for (int o = 0; o < kMelOctets; ++o) {
-    fb->mel_glo[o] = glo[o]; fb->mel_gcnt[o] = gcnt[o]; fb->mel_boff[o] = b;
+    boff[o] = b;
     for (int u = 0; u < gcnt[o]; ++u, ++b)
       for (int lane = 0; lane < 32; ++lane) {
         const int tig = lane & 3, gid = lane >> 2, k0 = 8 * (glo[o] + u) + 2 * tig, m = 8 * o + gid;
@@ -192,6 +193,74 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
         const float h0 = tf32_trunc(w[0]), h1 = tf32_trunc(w[1]);
         fb->mel_frag[(size_t)b * 32 + lane] = make_float4(h0, h1, tf32_trunc(w[0] - h0), tf32_trunc(w[1] - h1));
       }
+  }
+  // Deal the blocks to the 8 warps: walk the octets (heaviest end first) and cut the line of blocks into 8 runs of about equal
+  // cost.  Cost model (instructions per warp and round): a block ~ kBlk, the dB epilogue of an octet ~ kOut, a partial-sum
+  // hand-off ~ kXch.  A cut inside an octet makes the run that ends a warp's work the OWNER (it adds the partial sums and writes
+  // the dB values, last thing it does) and the continuation in the next warp(s) a PRODUCER (first thing that warp does), so an
+  // owner practically never waits.  At most two producers per octet.
+  constexpr int kBlk = 20, kOut = 30, kXch = 12;
+  struct Task { int oct, role, g_lo, g_cnt, aux; };         // aux: producer -> its slot
+  std::vector<Task> per_warp[kMelOctets];
+  int total = 0;
+  for (int o = 0; o < kMelOctets; ++o) total += kBlk * gcnt[o] + kOut;
+  bool ok = false;
+  for (int target = total / kMelOctets; target <= total + kOut && !ok; target += 4) {
+    for (int w = 0; w < kMelOctets; ++w) per_warp[w].clear();
+    int w = 0, load = 0;
+    ok = true;
+    for (int o = kMelOctets - 1; o >= 0 && ok; --o) {
+      int remaining = gcnt[o], g = glo[o], producers = 0;
+      bool owner_placed = false;
+      for (;;) {
+        const bool room = (int)per_warp[w].size() < 6;                          // runs per warp (8 octets: never reached)
+        const int fixed = owner_placed ? kXch : kOut;                       // cost of this part besides its blocks
+        if (room && load + kBlk * remaining + fixed <= target) {            // the rest of the octet fits here
+          per_warp[w].push_back({o, owner_placed ? kMelProducer : kMelWhole, g, remaining, producers});
+          load += kBlk * remaining + fixed;
+          break;
+        }
+        int n = room ? (target - load - fixed - (owner_placed ? 0 : kXch)) / kBlk : 0;
+        if (n > remaining - 1) n = remaining - 1;                           // something must be left for the next warp
+        if (n >= 1 && (!owner_placed || producers < 1)) {
+          per_warp[w].push_back({o, owner_placed ? kMelProducer : kMelOwner, g, n, producers});
+          producers += owner_placed;
+          owner_placed = true;
+          remaining -= n; g += n;
+        } else if (load == 0) {                             // an empty warp cannot take it and it cannot be cut (further)
+          ok = false; break;
+        }
+        if (++w == kMelOctets) { ok = false; break; }
+        load = 0;
+      }
+    }
+  }
+  if (!ok)                                                   // cannot happen (target = total always fits); keep a safe schedule anyway
+    for (int w = 0; w < kMelOctets; ++w) { per_warp[w].clear(); per_warp[w].push_back({w, kMelWhole, glo[w], gcnt[w], 0}); }
+  // emit the per-warp block lists
+  int prod_slot[kMelOctets][2], n_prod[kMelOctets] = {0}, next_slot = 0;
+  for (int w = 0; w < kMelOctets; ++w)
+    for (const Task& t : per_warp[w])
+      if (t.role == kMelProducer) prod_slot[t.oct][n_prod[t.oct]++] = next_slot++;
+  UITK_REQUIRE(next_slot <= kMelSlots, UITK_EINVAL, "mel schedule needs %d hand-off slots (max %d)", next_slot, kMelSlots);
+  for (int w = 0; w < kMelOctets; ++w) {
+    int n = 0;
+    for (int pass = 0; pass < 3; ++pass)                     // producers, whole octets, owners
+      for (const Task& t : per_warp[w]) {
+        if (t.role != (pass == 0 ? kMelProducer : pass == 1 ? kMelWhole : kMelOwner)) continue;
+        int aux = 0;
+        if (t.role == kMelProducer) aux = prod_slot[t.oct][t.aux] | (n_prod[t.oct] << 3);
+        if (t.role == kMelOwner) aux = n_prod[t.oct] | (prod_slot[t.oct][0] << 2) | ((n_prod[t.oct] > 1 ? prod_slot[t.oct][1] : 0) << 5);
+        const int cnt = t.g_cnt > 0 ? t.g_cnt : 1;           // an octet without weights: one all-zero block
+        UITK_REQUIRE(n + cnt <= kMelWarpBlocks, UITK_EINVAL, "mel schedule: more than %d blocks for one warp", kMelWarpBlocks);
+        for (int u = 0; u < cnt; ++u) {
+          const int fin = u == cnt - 1;
+          const int g = t.g_cnt > 0 ? t.g_lo + u : 0, blk = t.g_cnt > 0 ? boff[t.oct] + (t.g_lo - glo[t.oct]) + u : n_blocks;
+          fb->mel_blk[w][n++] = MelBlk{g | (fin << 8) | (fin ? (t.role << 9) | (t.oct << 11) | (aux << 14) : 0), blk};
+        }
+      }
+    fb->mel_nblk[w] = n;
+    if (n > 0) fb->mel_blk[w][n] = fb->mel_blk[w][n - 1];
   }
   return UITK_OK;
 }

@@ -33,29 +33,41 @@ void count_launches(int n);   // process-wide counter behind uitk_kernel_launche
 // ---------------------------------------------------------------------------------------------------------
 // Front-end constant blob (device layout).  All fields 4 bytes; header first.
 // ---------------------------------------------------------------------------------------------------------
-// Mel projection on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulate): the 64 mel bins are 8 octets (one per warp), the
-// 257 frequency bins are 33 groups of 8; octet o multiplies the groups [mel_glo[o], mel_glo[o] + mel_gcnt[o]) that hold its
-// non-zero filterbank entries.  For every (octet, group) the blob carries the B fragment of that 8x8 weight block, split
-// into tf32 hi + lo: entry [lane] = (b0_hi, b1_hi, b0_lo, b1_lo) with b0 = W[8g + 2*(lane%4)][8o + lane/4],
-// b1 = W[8g + 2*(lane%4) + 1][8o + lane/4], W = 0.25 * fb (the kernel keeps the power spectrum as 4 |X|^2).
+// Mel projection on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulate): the 64 mel bins are 8 octets, the 257 frequency
+// bins 33 groups of 8; octet o multiplies the groups that hold its non-zero filterbank entries.  For every (octet, group) the
+// blob carries the B fragment of that 8x8 weight block, split into tf32 hi + lo: entry [lane] = (b0_hi, b1_hi, b0_lo, b1_lo) with
+// b0 = W[8g + 2*(lane%4)][8o + lane/4], b1 = W[8g + 2*(lane%4) + 1][8o + lane/4], W = 0.25 * fb (the kernel keeps the power
+// spectrum as 4 |X|^2).  The blocks are dealt to the 8 warps of a CTA as SEGMENTS (a run of groups of one octet) so that every
+// warp has about the same work: a heavy octet is cut in two or three, the earlier parts ("producers") hand their partial sums
+// to the last ("owner") through shared memory, added in a fixed order (own + slot 0 + slot 1): the sum does not depend on timing.
 constexpr int kMelOctets = 8;
 constexpr int kMelGroups = 33;                 // ceil(257 / 8); group 32 holds the Nyquist bin alone
+constexpr int kMelWarpBlocks = 40;             // blocks per warp (dense filterbank: 264 / 8 = 33)
+constexpr int kMelSlots = 8;                   // partial-sum slots (at most 7 cuts between 8 warps)
+enum { kMelWhole = 0, kMelProducer = 1, kMelOwner = 2 };
+
+// One weight block of a warp's list.  x = group | fin << 8 | role << 9 | octet << 11 | aux << 14, y = block index in mel_frag.
+// fin: the block ends a run; role / octet / aux say what to do with the sums then:
+//   whole     write the octet's dB values
+//   producer  aux = slot | producers << 3: store the partial sums to the slot, arrive on named barrier 1 + octet
+//   owner     aux = producers | slot0 << 2 | slot1 << 5: wait on the barrier, add slot0 (+ slot1), write the dB values
+struct MelBlk {
+  int x, y;
+};
 
 struct FrontendBlob {
-  int magic;                 // 'UFE2'
-  int n_blocks;              // (octet, group) weight blocks that follow the fixed part
+  int magic;                 // 'UFE4'
+  int n_blocks;              // (octet, group) weight blocks that follow the fixed part (+ one all-zero block at index n_blocks)
   int pad0, pad1;
   float window[512];         // front_end.0.spectrogram.window
   float2 tw256[256];         // [k1*16 + lane] = exp(-2*pi*i*lane*k1/256)
   float2 tw512[256];         // exp(-2*pi*i*k/512)
-  int mel_glo[kMelOctets];   // first 8-bin group of octet o
-  int mel_gcnt[kMelOctets];  // number of groups
-  int mel_boff[kMelOctets];  // index of the octet's first block in mel_frag
-  int pad2[8];
-  float4 mel_frag[1];        // [n_blocks][32 lanes], variable length (>= 1)
+  int mel_nblk[kMelOctets];  // blocks of warp w (producer runs first, owner runs last: an owner never waits for a warp that waits)
+  MelBlk mel_blk[kMelOctets][kMelWarpBlocks + 1];   // entry [mel_nblk] repeats the last one (the kernel reads one ahead)
+  float4 mel_frag[1];        // [n_blocks + 1][32 lanes], variable length; the blocks of an octet are consecutive, groups ascending
 };
-inline size_t frontend_blob_bytes(int n_blocks) { return offsetof(FrontendBlob, mel_frag) + sizeof(float4) * 32 * (size_t)(n_blocks > 0 ? n_blocks : 1); }
-constexpr int kFrontendMagic = 0x55464532;
+inline size_t frontend_blob_bytes(int n_blocks) { return offsetof(FrontendBlob, mel_frag) + sizeof(float4) * 32 * (size_t)(n_blocks + 1); }
+constexpr int kFrontendMagic = 0x55464534;
 
 // ---------------------------------------------------------------------------------------------------------
 // Encoder blob (fp32 section).  Offsets in floats from the start of the fp32 section.
