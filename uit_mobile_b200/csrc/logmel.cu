@@ -87,13 +87,15 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 struct SmemLayout {
   float window[512];
-  float x[2][kStageFloats];          // double buffered: bulk copies stage round r+1 while round r computes
+  float x[kStageFloats];             // the round's samples; round r+1 is bulk-copied in while round r runs its mel phase
   float2 ex[kFramesPerRound * kExStride];   // per frame group: 16x17 transpose tile, then the frame's 257 powers (swizzled)
   float4 part[kMelSlots][32];        // partial mel sums of a split octet: producer warp(s) -> owner warp
-  MelBlk blk[kMelOctets][kMelWarpBlocks + 1];
+  MelBlk blk[kMelOctets][kMelWarpBlocks + 1];      // } contiguous, same order as in the blob: one copy loop
+  float2 w[kMelSmemBlocks][32];                    // } mel weight fragments
   float red[16];
-  uint64_t full[2];                  // mbarriers: "x[buf] landed"
+  uint64_t full;                     // mbarrier: "x landed"
 };
+static_assert(sizeof(MelBlk) * kMelOctets * (kMelWarpBlocks + 1) % 16 == 0, "block lists are copied as uint4");
 
 // TIn = float (the reference's input contract) or int16_t (PCM ingest: x = pcm / 32768, dataset.py:44-46 /
 // torchaudio.load normalisation; the 2^-15 scale is folded into the window, which is exact, so both instantiations
@@ -151,8 +153,11 @@ __device__ __forceinline__ float power_to_db(float x) {
   return 3.01029995663981195f * l;
 }
 
+#ifndef K1X
+#define K1X 0
+#endif
 template <typename TIn>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, K1X == 3 ? 2 : 3)
 logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, int t0, long long out_bs, long long out_ms,
               long long num_rounds, int straddle, int rpc,
               const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
@@ -163,7 +168,7 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
 
   const int tid = threadIdx.x;
-  const int g = tid >> 4;      // frame slot in the round
+  const int g = (tid >> 5) + ((tid & 16) >> 1);   // frame slot in the round: warp p runs slots p (lanes 0-15) and p + 8 (lanes 16-31)
   const int j = tid & 15;      // lane within the frame group
   const int rounds_per_clip = (T + kFramesPerRound - 1) / kFramesPerRound;
   const long long r_begin = (long long)blockIdx.x * rpc;
@@ -172,12 +177,18 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   constexpr bool kPcm = sizeof(TIn) == 2;
   constexpr int kVec = 16 / (int)sizeof(TIn);          // samples per 16 bytes
   if (tid == 0) {
-    tc::mbar_init(&S.full[0], 1);
-    tc::mbar_init(&S.full[1], 1);
+    tc::mbar_init(&S.full, 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < 512; i += kThreads) S.window[i] = kPcm ? blob->window[i] * (1.f / 32768.f) : blob->window[i];
-  for (int i = tid; i < kMelOctets * (kMelWarpBlocks + 1); i += kThreads) (&S.blk[0][0])[i] = (&blob->mel_blk[0][0])[i];
+  // block lists + weight fragments (the fragments only if they fit: a denser filterbank than HTK/64 is read from global memory)
+  const bool w_in_smem = blob->n_blocks + 1 <= kMelSmemBlocks;
+  {
+    const int n16 = (int)(sizeof(S.blk) / 16) + (w_in_smem ? (blob->n_blocks + 1) * 32 * (int)sizeof(float2) / 16 : 0);
+    const uint4* src = reinterpret_cast<const uint4*>(&blob->mel_blk[0][0]);
+    uint4* dst = reinterpret_cast<uint4*>(&S.blk[0][0]);
+    for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+  }
   __syncthreads();
 
   float tmax = 0.f, tmin = INFINITY;
@@ -186,14 +197,14 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   const float2 wj512 = blob->tw512[j];
   const int Li = (int)L;
 
-  // Stage the samples of round r into S.x[buf] (warp 0 only).  A round reads one sample range per clip it touches (two when it
+  // Stage the samples of round r into S.x (warp 0 only).  A round reads one sample range per clip it touches (two when it
   // straddles a clip boundary); the part of a range that lies inside its clip is ONE 1-D bulk copy (cp.async.bulk, completion
-  // on S.full[buf]) issued by lane 0, the few samples of the reflect padding at the clip edges (and everything, if the clip's
+  // on S.full) issued by lane 0, the few samples of the reflect padding at the clip edges (and everything, if the clip's
   // rows are not 16-byte aligned) are written by the warp's lanes with the reflect index map (no edge repeat).
-  auto stage = [&](long long r, RoundPos P, int buf) {
+  auto stage = [&](long long r, RoundPos P) {
     if (r >= r_end || tid >= 32) return;
     const Round R = round_at(P, T, B, straddle);
-    TIn* dst = reinterpret_cast<TIn*>(S.x[buf]);           // raw samples (PCM uses half of the buffer)
+    TIn* dst = reinterpret_cast<TIn*>(S.x);                // raw samples (PCM uses half of the buffer)
     const int lenA = UITK_HOP * (R.nA - 1) + UITK_N_FFT;
     int len[2], s0[2], lo[2], hi[2];
     len[0] = lenA; len[1] = R.nB > 0 ? UITK_HOP * (R.nB - 1) + UITK_N_FFT : 0;
@@ -209,12 +220,12 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
       tx += (uint32_t)(hi[p] - lo[p]) * (uint32_t)sizeof(TIn);
     }
     if (tid == 0) {
-      tc::mbar_arrive_expect_tx(&S.full[buf], tx);
+      tc::mbar_arrive_expect_tx(&S.full, tx);
 #pragma unroll
       for (int p = 0; p < 2; ++p)
         if (hi[p] > lo[p])
           tc::bulk_g2s(dst + (p ? lenA : 0) + lo[p], wav + (R.cA + p) * ld + s0[p] + lo[p], (uint32_t)(hi[p] - lo[p]) * (uint32_t)sizeof(TIn),
-                       &S.full[buf]);
+                       &S.full);
     }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -231,36 +242,34 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
     }
   };
   RoundPos pos = round_pos(r_begin, T, straddle, rounds_per_clip);
-  stage(r_begin, pos, 0);
+  stage(r_begin, pos);
 
   // mel phase: lane = 4 * gid + tig (mma fragment coordinates); this warp's segments of the filterbank (uitk_common.cuh)
   const int lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
   const int mel_nblk = blob->mel_nblk[warp];
-  const float4* const frag0 = blob->mel_frag + lane;
   const long long orow_tig = (long long)(2 * tig) * out_ms;
-  // Power rows: the two frame slots 2p, 2p + 1 of warp p share one row, bin-interleaved, that reuses the warp's transpose tiles:
-  // P[2p + h][k] at float 2 * (k ^ swz(p)) + h.  A 16-byte load at bins (b, b + 1) is then exactly the A fragment of mma rows
-  // p / p + 8 (= slots 2p / 2p + 1) for logical k = tig / tig + 4 <-> bins b = 8G + 2 tig, b + 1; the stores of a warp's two frame
-  // groups hit even / odd banks; the XOR (8 bins for odd p) keeps the two rows of a quarter-warp load in different bank halves.
+  // Power rows: the two frame slots p, p + 8 of warp p share one row, bin-interleaved, that reuses the warp's first transpose tile:
+  // P[p + 8 h][k] at float 2 * (k ^ swz(p)) + h.  A 16-byte load at bins (b, b + 1) is then exactly the A fragment of mma rows
+  // p / p + 8 for logical k = tig / tig + 4 <-> bins b = 8G + 2 tig, b + 1; the stores of a warp's two frame groups hit even / odd
+  // banks; the XOR (8 bins for odd p) keeps the two rows of a quarter-warp load in different bank halves.
   // k = j + 16 m  ->  (j ^ swz) + 16 m;  256 - k = (16 - j) + 16 (15 - m)  ->  ((16 - j) ^ swz) + 16 (15 - m)   (swz = 0 | 8, also for j = 0)
-  float* prow_w = reinterpret_cast<float*>(S.ex + (g & ~1) * kExStride) + (g & 1);
-  float* const pk_base = prow_w + 2 * (j ^ ((g & 2) << 2));
-  float* const pn_base = prow_w + 2 * ((16 - j) ^ ((g & 2) << 2));
-  const float* const prow_r = reinterpret_cast<const float*>(S.ex + 2 * gid * kExStride) + 4 * tig;   // group G at + 16 * (G ^ (gid & 1))
+  float* prow_w = reinterpret_cast<float*>(S.ex + (g & 7) * kExStride) + (g >> 3);
+  float* const pk_base = prow_w + 2 * (j ^ ((g & 1) << 3));
+  float* const pn_base = prow_w + 2 * ((16 - j) ^ ((g & 1) << 3));
+  const float* const prow_r = reinterpret_cast<const float*>(S.ex + gid * kExStride) + 4 * tig;   // group G at + 16 * (G ^ (gid & 1))
+  const float2* const wtab = (w_in_smem ? &S.w[0][0] : blob->mel_frag) + lane;
 
-  int buf = 0;
-  for (long long r = r_begin; r < r_end; ++r, buf ^= 1) {
+  for (long long r = r_begin; r < r_end; ++r) {
     const RoundPos pos_next = next_pos(pos, T, straddle);
-    stage(r + 1, pos_next, buf ^ 1);                   // buffer last read before the previous round's second barrier
-    tc::mbar_wait(&S.full[buf], (uint32_t)(((r - r_begin) >> 1) & 1));
-    __syncthreads();   // scalar-staged edge samples of S.x[buf] visible; previous round's power rows are consumed
-    const TIn* sx = reinterpret_cast<const TIn*>(S.x[buf]);
+    tc::mbar_wait(&S.full, (uint32_t)((r - r_begin) & 1));
+    __syncthreads();   // scalar-staged edge samples of S.x visible; previous round's power rows are consumed
+    const TIn* sx = reinterpret_cast<const TIn*>(S.x);
     const Round R = round_at(pos, T, B, straddle);
     pos = pos_next;
     const int n_live = R.nA + R.nB;
-    const bool warp_live = (g & ~1) < n_live;          // warp-uniform: the warp's first frame group is live
+    const bool warp_live = (g & 7) < n_live;           // warp-uniform: the warp's first frame group is live
 
-    if (warp_live) {
+    if (warp_live && K1X != 2 && K1X != 4 && K1X != 5 && K1X != 6) {
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
     float2 v[16];
     const TIn* xf = sx + g * UITK_HOP + (g >= R.nA ? kStraddleShift : 0);
@@ -322,35 +331,40 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
     if (j == 0) pk_base[32 * 8] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);   // X[128] = conj(Z[128])
     }   // warp_live
     __syncthreads();
+    stage(r + 1, pos);                                 // S.x is free: the next round's samples land under the mel phase
 
     // ---- mel projection on the tensor cores + dB.  D[16 frame slots][8 mel bins of an octet] = P[16][8 bins] * W[8 bins][8]
     // summed over the segment's bin groups; P and W as tf32 hi + lo, three products (hi*hi + lo*hi + hi*lo: ~2^-21 relative).
     // Every warp walks its list of weight blocks (uitk_common.cuh); a block with the fin bit ends a run of one octet.
-    {
+    if (K1X != 1 && K1X != 4) {
       long long orow[2];                               // output offsets (mel 2 tig of octet 0) of this lane's two frame slots
       const long long rowA = R.cA * out_bs + t0 + R.tA, rowB = (R.cA + 1) * out_bs + t0 - R.nA;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int s = 2 * gid + h;                     // mma rows gid / gid + 8 are frame slots 2 gid / 2 gid + 1
+        const int s = gid + 8 * h;                     // mma rows gid / gid + 8 are frame slots gid / gid + 8
         orow[h] = (s < R.nA ? rowA : rowB) + s + orow_tig;
       }
       const MelBlk* blk = S.blk[warp];
       MelBlk me = blk[0];
-      float4 wf = __ldg(frag0 + (size_t)me.y * 32);
+      float2 wf = wtab[me.y * 32];
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f}, acw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int b = 0; b < mel_nblk; ++b) {
         const MelBlk nx = blk[b + 1];
-        const float4 wn = __ldg(frag0 + (size_t)nx.y * 32);          // next block's weights under this block's math
-        // (P[2 gid][k], P[2 gid + 1][k], P[2 gid][k + 1], P[2 gid + 1][k + 1]), k = 8 G + 2 tig  ==  (a0, a1, a2, a3)
+        const float2 wn = wtab[nx.y * 32];                           // next block's weights under this block's math
+        // (P[gid][k], P[gid + 8][k], P[gid][k + 1], P[gid + 8][k + 1]), k = 8 G + 2 tig  ==  (a0, a1, a2, a3)
         const float4 pa = *reinterpret_cast<const float4*>(prow_r + 16 * ((me.x & 0xff) ^ (gid & 1)));
         const uint32_t a0 = __float_as_uint(pa.x) & 0xffffe000u, a1 = __float_as_uint(pa.y) & 0xffffe000u;
         const uint32_t a2 = __float_as_uint(pa.z) & 0xffffe000u, a3 = __float_as_uint(pa.w) & 0xffffe000u;
         const uint32_t l0 = __float_as_uint(pa.x - __uint_as_float(a0)), l1 = __float_as_uint(pa.y - __uint_as_float(a1));
         const uint32_t l2 = __float_as_uint(pa.z - __uint_as_float(a2)), l3 = __float_as_uint(pa.w - __uint_as_float(a3));
-        mma_tf32(acc, a0, a1, a2, a3, __float_as_uint(wf.x), __float_as_uint(wf.y));
-        mma_tf32(acl, l0, l1, l2, l3, __float_as_uint(wf.x), __float_as_uint(wf.y));
-        mma_tf32(acw, a0, a1, a2, a3, __float_as_uint(wf.z), __float_as_uint(wf.w));
+        const uint32_t b0 = __float_as_uint(wf.x) & 0xffffe000u, b1 = __float_as_uint(wf.y) & 0xffffe000u;
+        const uint32_t c0 = __float_as_uint(wf.x - __uint_as_float(b0)), c1 = __float_as_uint(wf.y - __uint_as_float(b1));
+        if (K1X != 6) {
+        mma_tf32(acc, a0, a1, a2, a3, b0, b1);
+        mma_tf32(acl, l0, l1, l2, l3, b0, b1);
+        mma_tf32(acw, a0, a1, a2, a3, c0, c1);
+        } else { acc[0] += pa.x * wf.x; acc[1] += pa.y * wf.y; acc[2] += pa.z; acc[3] += pa.w; }
         if (me.x & 0x100) {                            // end of a run (warp-uniform)
           const int role = (me.x >> 9) & 3, oct = (me.x >> 11) & 7, aux = me.x >> 14;
           float m[4];
@@ -371,12 +385,14 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (2 * gid + h < n_live) {
+              if (gid + 8 * h < n_live) {
                 float* o = db + orow[h] + (long long)(8 * oct) * out_ms;
                 const float m0 = m[2 * h], m1 = m[2 * h + 1];
                 tmax = fmaxf(tmax, fmaxf(m0, m1)); tmin = fminf(tmin, fminf(m0, m1));
+                if (K1X != 5) {
                 o[0] = power_to_db(m0);
                 o[out_ms] = power_to_db(m1);
+                }
               }
             }
           }

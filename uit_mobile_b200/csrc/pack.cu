@@ -147,14 +147,6 @@ static int mel_block_ranges(const float* h_fb, int* glo, int* gcnt) {
   return n;
 }
 
-static float tf32_trunc(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  u &= 0xffffe000u;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 size_t uitk_frontend_blob_bytes(const float* h_fb) {
   int glo[kMelOctets], gcnt[kMelOctets];
   return frontend_blob_bytes(h_fb ? mel_block_ranges(h_fb, glo, gcnt) : kMelOctets * kMelGroups);
@@ -189,9 +181,7 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
         float w[2];
         for (int e = 0; e < 2; ++e)       // x 1/4: the kernel keeps the power spectrum as 4 |X|^2 (exact scaling)
           w[e] = k0 + e < UITK_N_FREQS ? 0.25f * h_fb[(size_t)(k0 + e) * UITK_N_MELS + m] : 0.f;
-        // tf32 hi + lo split (11 + 11 significant bits; the tensor core ignores the low 13 bits of an operand)
-        const float h0 = tf32_trunc(w[0]), h1 = tf32_trunc(w[1]);
-        fb->mel_frag[(size_t)b * 32 + lane] = make_float4(h0, h1, tf32_trunc(w[0] - h0), tf32_trunc(w[1] - h1));
+        fb->mel_frag[(size_t)b * 32 + lane] = make_float2(w[0], w[1]);
       }
   }
   // Deal the blocks to the 8 warps: walk the octets (heaviest end first) and cut the line of blocks into 8 runs of about equal
@@ -199,7 +189,7 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
   // hand-off ~ kXch.  A cut inside an octet makes the run that ends a warp's work the OWNER (it adds the partial sums and writes
   // the dB values, last thing it does) and the continuation in the next warp(s) a PRODUCER (first thing that warp does), so an
   // owner practically never waits.  At most two producers per octet.
-  constexpr int kBlk = 20, kOut = 30, kXch = 12;
+  constexpr int kBlk = 24, kOut = 30, kXch = 12, kStage = 40;
   struct Task { int oct, role, g_lo, g_cnt, aux; };         // aux: producer -> its slot
   std::vector<Task> per_warp[kMelOctets];
   int total = 0;
@@ -207,7 +197,7 @@ int uitk_pack_frontend(const float* h_window, const float* h_fb, void* h_blob, s
   bool ok = false;
   for (int target = total / kMelOctets; target <= total + kOut && !ok; target += 4) {
     for (int w = 0; w < kMelOctets; ++w) per_warp[w].clear();
-    int w = 0, load = 0;
+    int w = 0, load = kStage;                               // warp 0 first issues the next round's staging copy
     ok = true;
     for (int o = kMelOctets - 1; o >= 0 && ok; --o) {
       int remaining = gcnt[o], g = glo[o], producers = 0;

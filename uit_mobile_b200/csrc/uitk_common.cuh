@@ -35,7 +35,7 @@ void count_launches(int n);   // process-wide counter behind uitk_kernel_launche
 // ---------------------------------------------------------------------------------------------------------
 // Mel projection on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulate): the 64 mel bins are 8 octets, the 257 frequency
 // bins 33 groups of 8; octet o multiplies the groups that hold its non-zero filterbank entries.  For every (octet, group) the
-// blob carries the B fragment of that 8x8 weight block, split into tf32 hi + lo: entry [lane] = (b0_hi, b1_hi, b0_lo, b1_lo) with
+// blob carries the B fragment of that 8x8 weight block in fp32 (the kernel splits it into tf32 hi + lo): entry [lane] = (b0, b1) with
 // b0 = W[8g + 2*(lane%4)][8o + lane/4], b1 = W[8g + 2*(lane%4) + 1][8o + lane/4], W = 0.25 * fb (the kernel keeps the power
 // spectrum as 4 |X|^2).  The blocks are dealt to the 8 warps of a CTA as SEGMENTS (a run of groups of one octet) so that every
 // warp has about the same work: a heavy octet is cut in two or three, the earlier parts ("producers") hand their partial sums
@@ -44,6 +44,8 @@ constexpr int kMelOctets = 8;
 constexpr int kMelGroups = 33;                 // ceil(257 / 8); group 32 holds the Nyquist bin alone
 constexpr int kMelWarpBlocks = 40;             // blocks per warp (dense filterbank: 264 / 8 = 33)
 constexpr int kMelSlots = 8;                   // partial-sum slots (at most 7 cuts between 8 warps)
+constexpr int kMelSmemBlocks = 48;             // weight blocks the kernel keeps in shared memory (HTK/64: 40 + the zero block); a
+                                               // denser filterbank is read from global memory instead
 enum { kMelWhole = 0, kMelProducer = 1, kMelOwner = 2 };
 
 // One weight block of a warp's list.  x = group | fin << 8 | role << 9 | octet << 11 | aux << 14, y = block index in mel_frag.
@@ -64,10 +66,10 @@ struct FrontendBlob {
   float2 tw512[256];         // exp(-2*pi*i*k/512)
   int mel_nblk[kMelOctets];  // blocks of warp w (producer runs first, owner runs last: an owner never waits for a warp that waits)
   MelBlk mel_blk[kMelOctets][kMelWarpBlocks + 1];   // entry [mel_nblk] repeats the last one (the kernel reads one ahead)
-  float4 mel_frag[1];        // [n_blocks + 1][32 lanes], variable length; the blocks of an octet are consecutive, groups ascending
+  float2 mel_frag[1];        // [n_blocks + 1][32 lanes], variable length; the blocks of an octet are consecutive, groups ascending
 };
-inline size_t frontend_blob_bytes(int n_blocks) { return offsetof(FrontendBlob, mel_frag) + sizeof(float4) * 32 * (size_t)(n_blocks + 1); }
-constexpr int kFrontendMagic = 0x55464534;
+inline size_t frontend_blob_bytes(int n_blocks) { return offsetof(FrontendBlob, mel_frag) + sizeof(float2) * 32 * (size_t)(n_blocks + 1); }
+constexpr int kFrontendMagic = 0x55464535;
 
 // ---------------------------------------------------------------------------------------------------------
 // Encoder blob (fp32 section).  Offsets in floats from the start of the fp32 section.
