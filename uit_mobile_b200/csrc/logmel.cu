@@ -5,14 +5,23 @@
 // The batch-global top-dB clamp (Q2) is NOT applied here: the kernel only tracks the global maximum.
 //
 // The B * T frames of the batch are one flat list cut into rounds of 16 consecutive frames (a round may straddle two
-// clips, so T = 101 wastes no frame slot); one CTA = 7 consecutive rounds, 3 CTAs per SM (75.9 KB of shared memory each).
-// A frame's 512-point real DFT is computed as a
-// 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) by 16 threads (half a warp), each holding 16 complex points in
-// registers: radix-16 pass over registers, W256 twiddle, 16x16 transpose through shared memory (warp-synchronous, padded
-// rows), second radix-16 pass, real-FFT unpack, |X|^2, sparse mel (<=2 non-zero filters per bin -> packed ranges), dB.
-// The samples of round r+1 are staged with 16-byte cp.async while round r computes.  HBM sees every sample once (frames
-// overlap 3.2x; the overlap is absorbed by the staging buffer / L1) and every output once: 4*L + 4*64*T algorithmic
-// bytes/clip.
+// clips, so T = 101 wastes no frame slot); one CTA = 7 consecutive rounds, 256 threads, 3 CTAs per SM (70 KB of shared memory each).
+// Per round:
+//  * staging: the round's <= 3264 samples arrive with one or two 1-D bulk copies (cp.async.bulk + mbarrier, issued by one
+//    lane while the previous round runs its mel phase); only the reflect padding at the clip edges is written by threads.
+//  * FFT phase: a frame's 512-point real DFT is a 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) by 16 threads (half a warp),
+//    16 complex points each in registers: radix-16 pass, W256 twiddle, 16x16 transpose through padded shared memory
+//    (warp-synchronous), second radix-16 pass, real-FFT unpack two bins at a time (k and 256 - k share one partner shuffle),
+//    |X|^2 stored as the frame's power row.
+//  * mel phase: P[16 frames][257] x W[257][64] on the tensor cores (mma.sync m16n8k8 tf32; both operands split hi + lo, three
+//    products, fp32 accumulate: ~2^-21 relative).  Only the 40 8x8 blocks of W that hold filterbank entries are multiplied; they
+//    are dealt to the 8 warps as balanced runs at pack time (uitk_common.cuh).  The A fragments come straight out of the
+//    bin-interleaved, XOR-swizzled power rows (one conflict-free 16-byte load per block), the dB values go from the
+//    accumulator fragments to global memory in 32-byte runs.
+// HBM sees every sample once (frames overlap 3.2x; the overlap is absorbed by the staging buffer) and every output once:
+// 4*L + 4*64*T algorithmic bytes/clip.  The legacy mma.sync path is deliberate: the contraction is 0.5 % of a tensor core's
+// time either way; what it buys is that the 2 x 257 power / weight values per frame no longer cross the LSU twice (the
+// CUDA-core version of this phase was 48 % of the kernel's shared-memory wavefronts).
 #include "tc_ptx.cuh"
 #include "uitk_common.cuh"
 
@@ -85,18 +94,6 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
   t = v[11]; v[11] = v[14]; v[14] = t;
 }
 
-struct SmemLayout {
-  float window[512];
-  float x[kStageFloats];             // the round's samples; round r+1 is bulk-copied in while round r runs its mel phase
-  float2 ex[kFramesPerRound * kExStride];   // per frame group: 16x17 transpose tile, then the frame's 257 powers (swizzled)
-  float4 part[kMelSlots][32];        // partial mel sums of a split octet: producer warp(s) -> owner warp
-  MelBlk blk[kMelOctets][kMelWarpBlocks + 1];      // } contiguous, same order as in the blob: one copy loop
-  float2 w[kMelSmemBlocks][32];                    // } mel weight fragments
-  float red[16];
-  uint64_t full;                     // mbarrier: "x landed"
-};
-static_assert(sizeof(MelBlk) * kMelOctets * (kMelWarpBlocks + 1) % 16 == 0, "block lists are copied as uint4");
-
 // TIn = float (the reference's input contract) or int16_t (PCM ingest: x = pcm / 32768, dataset.py:44-46 /
 // torchaudio.load normalisation; the 2^-15 scale is folded into the window, which is exact, so both instantiations
 // produce bit-identical results for the same audio).
@@ -106,6 +103,7 @@ static_assert(sizeof(MelBlk) * kMelOctets * (kMelWarpBlocks + 1) % 16 == 0, "blo
 struct Round {
   long long cA;     // first clip
   int tA, nA, nB;   // first frame in cA, live slots in cA, live slots in cA + 1
+  int pad;
 };
 // (clip, first frame) of a round; stepped from round to round without divisions (one 64-bit division per CTA)
 struct RoundPos {
@@ -137,6 +135,19 @@ __device__ __forceinline__ Round round_at(RoundPos P, int T, long long B, int st
   return R;
 }
 
+struct SmemLayout {
+  float window[512];
+  float x[kStageFloats];             // the round's samples; round r+1 is bulk-copied in while round r runs its mel phase
+  float2 ex[kFramesPerRound * kExStride];   // per frame group: 16x17 transpose tile, then the frame's 257 powers (swizzled)
+  float4 part[kMelSlots][32];        // partial mel sums of a split octet: producer warp(s) -> owner warp
+  MelBlk blk[kMelOctets][kMelWarpBlocks + 1];      // } contiguous, same order as in the blob: one copy loop
+  float2 w[kMelSmemBlocks][32];                    // } mel weight fragments
+  float red[16];
+  Round desc[2];                     // where the frame slots of the round come from (written by warp 0 with the staging)
+  uint64_t full;                     // mbarrier: "x landed"
+};
+static_assert(sizeof(MelBlk) * kMelOctets * (kMelWarpBlocks + 1) % 16 == 0, "block lists are copied as uint4");
+
 // D(16x8, fp32) += A(16x8, tf32, row) * B(8x8, tf32, col).  Fragments (lane = 4 * gid + tig): a0 = A[gid][tig], a1 = A[gid+8][tig],
 // a2 = A[gid][tig+4], a3 = A[gid+8][tig+4]; b0 = B[tig][gid], b1 = B[tig+4][gid]; d0/d1 = D[gid][2 tig, +1], d2/d3 = D[gid+8][..].
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -153,11 +164,8 @@ __device__ __forceinline__ float power_to_db(float x) {
   return 3.01029995663981195f * l;
 }
 
-#ifndef K1X
-#define K1X 0
-#endif
 template <typename TIn>
-__global__ void __launch_bounds__(kThreads, K1X == 3 ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, 3)
 logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long ld, int T, int t0, long long out_bs, long long out_ms,
               long long num_rounds, int straddle, int rpc,
               const FrontendBlob* __restrict__ blob, float* __restrict__ db, uint32_t* __restrict__ max_pow,
@@ -204,6 +212,7 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   auto stage = [&](long long r, RoundPos P) {
     if (r >= r_end || tid >= 32) return;
     const Round R = round_at(P, T, B, straddle);
+    if (tid == 0) S.desc[(r - r_begin) & 1] = R;
     TIn* dst = reinterpret_cast<TIn*>(S.x);                // raw samples (PCM uses half of the buffer)
     const int lenA = UITK_HOP * (R.nA - 1) + UITK_N_FFT;
     int len[2], s0[2], lo[2], hi[2];
@@ -260,16 +269,15 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
   const float2* const wtab = (w_in_smem ? &S.w[0][0] : blob->mel_frag) + lane;
 
   for (long long r = r_begin; r < r_end; ++r) {
-    const RoundPos pos_next = next_pos(pos, T, straddle);
     tc::mbar_wait(&S.full, (uint32_t)((r - r_begin) & 1));
-    __syncthreads();   // scalar-staged edge samples of S.x visible; previous round's power rows are consumed
+    __syncthreads();   // scalar-staged edge samples of S.x and the round descriptor visible; previous round's power rows are consumed
     const TIn* sx = reinterpret_cast<const TIn*>(S.x);
-    const Round R = round_at(pos, T, B, straddle);
-    pos = pos_next;
+    const Round R = S.desc[(r - r_begin) & 1];
+    if (tid < 32) pos = next_pos(pos, T, straddle);    // only the staging warp tracks the position
     const int n_live = R.nA + R.nB;
     const bool warp_live = (g & 7) < n_live;           // warp-uniform: the warp's first frame group is live
 
-    if (warp_live && K1X != 2 && K1X != 4 && K1X != 5 && K1X != 6) {
+    if (warp_live) {
     // ---- windowed load: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], n = j + 16 m
     float2 v[16];
     const TIn* xf = sx + g * UITK_HOP + (g >= R.nA ? kStraddleShift : 0);
@@ -330,13 +338,16 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
     }
     if (j == 0) pk_base[32 * 8] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);   // X[128] = conj(Z[128])
     }   // warp_live
+    const MelBlk* blk = S.blk[warp];
+    MelBlk me = blk[0];                                // first weight block of the mel phase: loaded under the barrier wait
+    float2 wf = wtab[me.y * 32];
     __syncthreads();
     stage(r + 1, pos);                                 // S.x is free: the next round's samples land under the mel phase
 
     // ---- mel projection on the tensor cores + dB.  D[16 frame slots][8 mel bins of an octet] = P[16][8 bins] * W[8 bins][8]
     // summed over the segment's bin groups; P and W as tf32 hi + lo, three products (hi*hi + lo*hi + hi*lo: ~2^-21 relative).
     // Every warp walks its list of weight blocks (uitk_common.cuh); a block with the fin bit ends a run of one octet.
-    if (K1X != 1 && K1X != 4) {
+    {
       long long orow[2];                               // output offsets (mel 2 tig of octet 0) of this lane's two frame slots
       const long long rowA = R.cA * out_bs + t0 + R.tA, rowB = (R.cA + 1) * out_bs + t0 - R.nA;
 #pragma unroll
@@ -344,9 +355,6 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
         const int s = gid + 8 * h;                     // mma rows gid / gid + 8 are frame slots gid / gid + 8
         orow[h] = (s < R.nA ? rowA : rowB) + s + orow_tig;
       }
-      const MelBlk* blk = S.blk[warp];
-      MelBlk me = blk[0];
-      float2 wf = wtab[me.y * 32];
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f}, acw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int b = 0; b < mel_nblk; ++b) {
@@ -360,11 +368,9 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
         const uint32_t l2 = __float_as_uint(pa.z - __uint_as_float(a2)), l3 = __float_as_uint(pa.w - __uint_as_float(a3));
         const uint32_t b0 = __float_as_uint(wf.x) & 0xffffe000u, b1 = __float_as_uint(wf.y) & 0xffffe000u;
         const uint32_t c0 = __float_as_uint(wf.x - __uint_as_float(b0)), c1 = __float_as_uint(wf.y - __uint_as_float(b1));
-        if (K1X != 6) {
         mma_tf32(acc, a0, a1, a2, a3, b0, b1);
         mma_tf32(acl, l0, l1, l2, l3, b0, b1);
         mma_tf32(acw, a0, a1, a2, a3, c0, c1);
-        } else { acc[0] += pa.x * wf.x; acc[1] += pa.y * wf.y; acc[2] += pa.z; acc[3] += pa.w; }
         if (me.x & 0x100) {                            // end of a run (warp-uniform)
           const int role = (me.x >> 9) & 3, oct = (me.x >> 11) & 7, aux = me.x >> 14;
           float m[4];
@@ -389,10 +395,8 @@ logmel_kernel(const TIn* __restrict__ wav, long long B, long long L, long long l
                 float* o = db + orow[h] + (long long)(8 * oct) * out_ms;
                 const float m0 = m[2 * h], m1 = m[2 * h + 1];
                 tmax = fmaxf(tmax, fmaxf(m0, m1)); tmin = fminf(tmin, fminf(m0, m1));
-                if (K1X != 5) {
                 o[0] = power_to_db(m0);
                 o[out_ms] = power_to_db(m1);
-                }
               }
             }
           }
