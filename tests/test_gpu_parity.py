@@ -334,3 +334,24 @@ def test_errors_are_loud():
             m(torch.zeros(2, 16000, device=DEV))
     finally:
         m.eval()
+
+
+def test_batch_pipeline_equals_forward():
+    """BatchPipeline (front-end of batch i+1 on one stream under the encoder of batch i on another) returns, batch by batch, the
+    bits of model(x); a held result survives until `depth` more submissions; shapes may change between batches."""
+    from uit_mobile_b200.pipeline import BatchPipeline
+    m = model("uit_xs", precision="bf16")
+    xs = [torch.from_numpy(H.noise_clips(b, L, seed=300 + i)).to(DEV) for i, (b, L) in enumerate([(37, 16000), (37, 16000), (12, 16000), (5, 32000), (37, 16000)])]
+    want = [m(x).clone() for x in xs]
+    pipe = BatchPipeline(m, depth=2)
+    tickets, got = [], []
+    for i, x in enumerate(xs):
+        tickets.append(pipe.submit(x))
+        if i >= 1:
+            got.append(pipe.result(tickets[i - 1]).clone())
+    got.append(pipe.result(tickets[-1]).clone())
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])

@@ -532,23 +532,23 @@ class UITBase(nn.Module):
         crops = int(N.lib().uitk_num_crops(T, self.target_length))
         return 5 // math.gcd(5, crops)
 
-    def _finish(self, db: torch.Tensor, words: torch.Tensor) -> torch.Tensor:
+    def _finish(self, db: torch.Tensor, words: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Encoder + head given the un-clamped log-mel and the [max, min] power words of THIS rank's clips (Q2)."""
         max_w, min_w = words[0:1], words[1:2]
         if self.process_group is None:
-            return self.encode(db, max_w)
+            return self.encode(db, max_w, out=out)
         dist = torch.distributed
         if not self._cfg().tensor_core:
             # fp32 / variant kernels: the batch-global cutoff first (blocking all-reduce of one word), then the encoder
             dist.all_reduce(max_w, op=dist.ReduceOp.MAX, group=self.process_group)
-            return self.encode(db, max_w)
+            return self.encode(db, max_w, out=out)
         # Sharded, tensor-core configuration: NO collective on the critical path.  Encode speculatively with the rank-local
         # maximum while the all-reduce(MAX) of [max, -1 - min] (non-negative floats order like their int32 bit patterns) runs on
         # the NCCL stream, then launch the device-conditional exact re-run: its kernels return at once unless this rank's
         # cutoff was below the global one AND one of its values lies under the global cutoff (uitk_encoder_fixup).
         g = torch.stack((words[0], -1 - words[1]))
         work = dist.all_reduce(g, op=dist.ReduceOp.MAX, group=self.process_group, async_op=True)
-        probs = self.encode(db, max_w) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
+        probs = self.encode(db, max_w, out=out) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
         work.wait()
         if db.shape[0]:
             self.encode(db, g[0:1], out=probs, fixup=(max_w, min_w))

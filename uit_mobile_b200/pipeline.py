@@ -199,3 +199,82 @@ class FrontEndHostPipeline:
         self.h2d_bytes = B * self.L * 4
         self.d2h_bytes = self.out_host[:B].numel() * 4 + 8
         return self.out_host[:B]
+
+
+class BatchPipeline:
+    """Device-resident batches, two in flight: the front-end kernel (K1) of batch i+1 runs on its own stream while the encoder
+    (K2 + head) of batch i drains on another, so the SMs that the persistent encoder CTAs leave idle in their last tile wave
+    (820 tiles over 296 CTAs at 4096 clips) take log-mel CTAs of the next batch, and the encoder CTAs of batch i+1 start on
+    SMs as the log-mel grid runs out.  Every batch is computed by exactly the kernels (and in the order) ``model.forward``
+    uses - the scores are bit-identical - only the launches of consecutive batches are no longer serialised.
+
+        t = pipe.submit(x)           # x: CUDA [B, L]; must stay unchanged until result(t)
+        ...                          # submit the next batch before asking for this one
+        y = pipe.result(t)           # CUDA [B, outputdim]; valid until `depth` more batches were submitted
+
+    ``result`` orders the caller's current stream behind the batch (no host synchronisation)."""
+
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, timing: bool = False):
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise N.UitkError("BatchPipeline needs the model on a CUDA device (no CPU fallback)")
+        if depth < 2:
+            raise ValueError("depth must be >= 2 (one batch in the front-end, one in the encoder)")
+        self.depth = depth
+        self.fe_stream = torch.cuda.Stream(self.device)
+        self.enc_stream = torch.cuda.Stream(self.device)
+        ev = lambda: torch.cuda.Event(enable_timing=timing)
+        self.slots = [dict(db=None, words=None, probs=None, fe_start=ev(), fe_done=ev(), enc_done=ev(), ticket=-1) for _ in range(depth)]
+        self.n = 0
+
+    @torch.no_grad()
+    def submit(self, x: torch.Tensor, wait_current: bool = True) -> int:
+        m = self.model
+        m._check_ready(x, "BatchPipeline.submit")
+        if x.dim() != 2:
+            raise ValueError(f"expected a [B, L] waveform batch, got shape {tuple(x.shape)}")
+        slot = self.slots[self.n % self.depth]
+        B, L = x.shape
+        T = int(N.lib().uitk_num_frames(L))
+        if slot["db"] is None or tuple(slot["db"].shape) != (B, 64, T):
+            # (re)allocated on the front-end stream, which is also the stream that first writes them
+            for old in (slot["db"], slot["probs"]):
+                if old is not None:
+                    old.record_stream(self.enc_stream)
+            with torch.cuda.stream(self.fe_stream):
+                slot["db"] = torch.empty((B, 64, T), dtype=torch.float32, device=self.device)
+                slot["probs"] = torch.empty((B, m.outputdim), dtype=torch.float32, device=self.device)
+        if wait_current:
+            self.fe_stream.wait_stream(torch.cuda.current_stream(self.device))      # x was produced on the caller's stream
+        with torch.cuda.stream(self.fe_stream):
+            if slot["ticket"] >= 0:
+                self.fe_stream.wait_event(slot["enc_done"])                          # the slot's previous batch has left the encoder
+            slot["fe_start"].record(self.fe_stream)
+            words = m._new_words(self.device)
+            if B:
+                m.front_end.logmel_unclamped(x, out=slot["db"], max_pow=words[0:1], min_pow=words[1:2])
+            slot["fe_done"].record(self.fe_stream)
+        with torch.cuda.stream(self.enc_stream):
+            self.enc_stream.wait_event(slot["fe_done"])
+            words.record_stream(self.enc_stream)
+            if B:
+                m._finish(slot["db"], words, out=slot["probs"])
+            elif m.process_group is not None:      # an empty shard still joins the collective of its group
+                m._finish(torch.empty((0, 64, 1), dtype=torch.float32, device=self.device), words)
+            slot["enc_done"].record(self.enc_stream)
+        slot["ticket"] = self.n
+        self.n += 1
+        return slot["ticket"]
+
+    def result(self, ticket: int) -> torch.Tensor:
+        slot = self.slots[ticket % self.depth]
+        if slot["ticket"] != ticket:
+            raise ValueError(f"batch {ticket} is no longer held (only the last {self.depth} submitted batches are)")
+        torch.cuda.current_stream(self.device).wait_event(slot["enc_done"])
+        return slot["probs"]
+
+    def events(self, ticket: int):
+        """(front-end start, front-end done, encoder done) events of a held batch (timing=True to read durations)."""
+        slot = self.slots[ticket % self.depth]
+        return slot["fe_start"], slot["fe_done"], slot["enc_done"]
