@@ -266,7 +266,7 @@ def run_b200(args):
 
     torch.manual_seed(0)                                        # identical random-init weights on every rank
     model = getattr(U.models, arch)(outputdim=537, target_length=102, precision=args.precision).to(dev).eval()
-    if world > 1:
+    if world > 1 and args.diag != "nogroup":
         model.process_group = dist.group.WORLD
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
@@ -285,11 +285,21 @@ def run_b200(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     pending = [None]      # in-flight all-gather of the previous step (NCCL stream): overlaps the next step's kernels
 
+    peer = [None, "nccl all_gather_into_tensor"]      # PeerGather (copy engines over NVLink peer memory) once the shard sizes are known
+
     def gather_async(probs, total, sizes_equal=True):
         """all-gather of the scores, left in flight: it is waited for at the start of the NEXT step's gather (and drained inside
-        the timed region after the last step)."""
+        the timed region after the last step).  Copy-engine pulls over NVLink peer memory when the group can map it, else NCCL."""
         if pending[0] is not None:
             pending[0][1].wait()
+        if peer[0] is not None:
+            out, done = peer[0](probs)
+
+            class _W:
+                def wait(self_inner):
+                    torch.cuda.current_stream().wait_event(done)
+            pending[0] = (out, _W(), probs)
+            return out
         out = torch.empty((total, probs.shape[1]), dtype=probs.dtype, device=dev)
         pending[0] = (out, dist.all_gather_into_tensor(out, probs, async_op=True), probs)
         return out
@@ -335,6 +345,13 @@ def run_b200(args):
         g_align = align
     equal_shards = len(set(shard_sizes)) == 1
     last_local = [None]
+    if world > 1 and kind != "frontend" and not args.nccl_gather:
+        try:
+            peer[0] = sharding.PeerGather(shard_sizes, 537, dist.group.WORLD, dev, depth=2)
+            peer[1] = "PeerGather: copy-engine pulls over NVLink peer memory (torch symmetric memory), no SMs"
+            equal_shards = True                       # PeerGather takes ragged shards as they are
+        except Exception as e:                        # no peer mapping on this box: NCCL
+            peer[1] = f"nccl all_gather (PeerGather unavailable: {type(e).__name__}: {str(e)[:120]})"
 
     def step(marks=None):
         with torch.no_grad():
@@ -403,12 +420,12 @@ def run_b200(args):
                 if prev is not None:
                     y = bp.result(prev)
                     last_local[0] = y
-                    if world > 1:
+                    if world > 1 and args.diag != "nogather":
                         gather_async(y, total) if equal_shards else sharding.gather_scores(y, total, align=g_align)
                 prev = t
             y = bp.result(prev)
             last_local[0] = y
-            if world > 1:
+            if world > 1 and args.diag != "nogather":
                 gather_async(y, total) if equal_shards else sharding.gather_scores(y, total, align=g_align)
             drain()
 
@@ -523,7 +540,7 @@ def run_b200(args):
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms,
         "timed_region": ("BatchPipeline: two batches in flight (front-end of step i+1 under the encoder tail of step i)" if pipelined
                          else "launches serialised on one stream"),
-        "sequential": sequential,
+        "sequential": sequential, "score_gather": peer[1] if world > 1 else None, **({"diag_INVALID_AS_BENCH": args.diag} if args.diag else {}),
     }
     if e2e16:
         line["e2e_int16_pcm"] = e2e16
@@ -667,6 +684,8 @@ def main():
     ap.add_argument("--precision", choices=["fp32", "bf16"], default=os.environ.get("UITK_PRECISION", "bf16"))
     ap.add_argument("--chunk", type=int, default=512, help="host pipeline chunk (clips)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diag", choices=["", "nogather", "nogroup"], default="", help="multi-GPU diagnosis: drop the score gather / the max-word exchange (NOT a valid bench line)")
+    ap.add_argument("--nccl-gather", action="store_true", help="gather the scores with NCCL instead of PeerGather")
     ap.add_argument("--no-pipeline", action="store_true", help="time the serialised launches only (no BatchPipeline pass)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys of the headline line (10 s front-end, sliding, comparators)")
     args = ap.parse_args()

@@ -22,9 +22,31 @@ with torch.no_grad():
     b, e = sharding.shard_bounds(total, rank, world, align)
     got = sharding.sharded_forward(model, x[b:e].to(dev), total, align=align)
 ok = torch.equal(ref, got)
+# the same gather with the copy engines over NVLink peer memory (sharding.PeerGather), twice (slot reuse), ragged shards
+peer_note = "PeerGather"
+try:
+    sizes = [sharding.shard_bounds(total, r, world, align)[1] - sharding.shard_bounds(total, r, world, align)[0] for r in range(world)]
+    pg = sharding.PeerGather(sizes, 537, dist.group.WORLD, dev)
+    model.process_group = dist.group.WORLD
+    for rep in range(3):
+        with torch.no_grad():
+            out, done = pg(model(x[b:e].to(dev)))
+        torch.cuda.current_stream().wait_event(done)
+        ok = ok and torch.equal(ref, out)
+    # BatchPipeline under a process group (async max all-reduce + conditional re-run on the encoder stream)
+    from uit_mobile_b200.pipeline import BatchPipeline
+    bp = BatchPipeline(model, depth=2)
+    xl = x[b:e].to(dev)
+    t0 = bp.submit(xl); t1 = bp.submit(xl)
+    for t in (t0, t1):
+        out, done = pg(bp.result(t))
+        torch.cuda.current_stream().wait_event(done)
+        ok = ok and torch.equal(ref, out)
+except Exception as exc:                                   # no peer mapping on this box
+    peer_note = f"PeerGather unavailable ({type(exc).__name__}: {str(exc)[:100]})"
 t = torch.tensor([int(ok)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"shard invariance over {world} GPUs ({total} clips, ragged): {'BIT-EXACT' if t.item() else 'MISMATCH'}; "
-          f"max|d| = {(ref - got).abs().max().item():.3e}")
+    print(f"shard invariance over {world} GPUs ({total} clips, ragged; NCCL gather, {peer_note}, BatchPipeline): "
+          f"{'BIT-EXACT' if t.item() else 'MISMATCH'}; max|d| = {(ref - got).abs().max().item():.3e}")
 dist.destroy_process_group()
 sys.exit(0 if t.item() else 1)

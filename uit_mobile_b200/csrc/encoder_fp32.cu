@@ -587,32 +587,37 @@ __global__ void __launch_bounds__(256) head_pooled_kernel(const float* __restric
 }
 }  // namespace
 
-// Single-crop head: probs[B][outputdim] = sigmoid(LayerNorm_1e-5(pooled[B][128]) W^T + b) as one fp32 GEMM.
-// 64 clips x 64 classes per CTA, the whole K = 128 resident in shared memory (one load phase, no k-loop barriers),
-// 4 x 4 outputs per thread.  576 CTAs for 4096 clips: the first version (128 x 128 tiles, 160 CTAs) left most SMs with one
-// 8-warp CTA and took 54 us of the encoder's 460; this one is latency-hidden by 3-4 resident CTAs per SM.
+// Single-crop head: probs[B][outputdim] = sigmoid(LayerNorm_1e-5(pooled[B][128]) W^T + b) as one GEMM on the tensor cores
+// (mma.sync m16n8k8 tf32; the fp32 CUDA-core version of round 1 took 35 us of the encoder's 435), both operands split
+// hi + lo and three products per k-step (hi*hi + lo*hi + hi*lo: ~2^-21 relative, i.e. fp32-grade logits in front of the sigmoid).
+// 64 clips x 64 classes per CTA of 4 warps; warp w normalises and multiplies its own 16 rows, so the CTA needs no barrier.  The
+// weight fragments come pre-split and in fragment order from the blob (pack.cu), one 16-byte load per lane, k-step and n-tile,
+// loaded one k-step ahead.  35 us -> see profiles/README.md.
 namespace {
-constexpr int kHM = 64, kHN = 64, kHLd = 132;
-__global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ pooled, int B, const float* __restrict__ hln_w,
-                                                        const float* __restrict__ hln_b, const float* __restrict__ head_wt,
-                                                        const float* __restrict__ head_b, int outputdim, int ld_head,
-                                                        float* __restrict__ probs, const uint32_t* c_true, const uint32_t* c_used,
-                                                        const uint32_t* c_min) {
+constexpr int kTLd = 136;      // row stride of the normalised features: 8 (mod 32) floats, so the 8-byte fragment loads are conflict-free
+__device__ __forceinline__ void mma_tf32_acc(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) head_tc_kernel(const float* __restrict__ pooled, int B, const float* __restrict__ hln_w,
+                                                      const float* __restrict__ hln_b, const float4* __restrict__ head_frag,
+                                                      const float* __restrict__ head_b, int outputdim, float* __restrict__ probs,
+                                                      const uint32_t* c_true, const uint32_t* c_used, const uint32_t* c_min) {
   if (c_used != nullptr && !fixup_needed(c_true, c_used, c_min)) return;      // uitk_encoder_fixup: nothing could differ
-  extern __shared__ __align__(16) float hs[];
-  float* As = hs;                      // [64][132] normalised features
-  float* Ws = hs + kHM * kHLd;         // [128][64] weight tile (k-major rows)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.x * kHM, n0 = blockIdx.y * kHN;
-  for (int idx = tid; idx < 128 * (kHN / 4); idx += 256) {
-    const int k = idx >> 4, c4 = idx & 15;
-    *reinterpret_cast<float4*>(&Ws[k * kHN + c4 * 4]) = __ldg(reinterpret_cast<const float4*>(head_wt + (size_t)k * ld_head + n0 + c4 * 4));
-  }
+  __shared__ __align__(16) float As[64 * kTLd];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  const int row0 = blockIdx.x * 64 + warp * 16, ct = blockIdx.y;
+  const float4* fr = head_frag + (size_t)ct * 16 * 8 * 32 + lane;
+  float4 bcur[8], bnext[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bcur[j] = __ldg(fr + j * 32);
   const float4 hg = __ldg(reinterpret_cast<const float4*>(hln_w + lane * 4));
   const float4 hb = __ldg(reinterpret_cast<const float4*>(hln_b + lane * 4));
-#pragma unroll
-  for (int i = 0; i < kHM / 8; ++i) {               // warp w normalises rows w*8 .. w*8+7 (one float4 per lane)
-    const int r = warp * (kHM / 8) + i, row = row0 + r;
+  float* Aw = As + warp * 16 * kTLd;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {                    // LayerNorm(1e-5) of this warp's 16 rows (one float4 per lane)
+    const int row = row0 + i;
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < B) m = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)row * 128 + lane * 4));
     float sum = m.x + m.y + m.z + m.w;
@@ -624,41 +629,46 @@ __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
-    *reinterpret_cast<float4*>(&As[r * kHLd + lane * 4]) =
+    *reinterpret_cast<float4*>(&Aw[i * kTLd + lane * 4]) =
         make_float4(d0 * rstd * hg.x + hb.x, d1 * rstd * hg.y + hb.y, d2 * rstd * hg.z + hb.z, d3 * rstd * hg.w + hb.w);
   }
-  __syncthreads();
-  float acc[4][4];
+  __syncwarp();
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const float* a_lo_row = Aw + gid * kTLd + 2 * tig;       // logical k = tig / tig + 4  <->  features 8 s + 2 tig, + 1
+  const float* a_hi_row = a_lo_row + 8 * kTLd;
+#pragma unroll 1
+  for (int s = 0; s < 16; ++s) {
+    if (s + 1 < 16) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < 128; k += 4) {
-    float4 a[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty * 4 + i) * kHLd + k]);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float4 b = *reinterpret_cast<const float4*>(&Ws[(k + kk) * kHN + tx * 4]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
-        acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
-        acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
-      }
+      for (int j = 0; j < 8; ++j) bnext[j] = __ldg(fr + ((s + 1) * 8 + j) * 32);
     }
+    const float2 p0 = *reinterpret_cast<const float2*>(a_lo_row + 8 * s), p1 = *reinterpret_cast<const float2*>(a_hi_row + 8 * s);
+    const uint32_t a0 = __float_as_uint(p0.x) & 0xffffe000u, a1 = __float_as_uint(p1.x) & 0xffffe000u;
+    const uint32_t a2 = __float_as_uint(p0.y) & 0xffffe000u, a3 = __float_as_uint(p1.y) & 0xffffe000u;
+    const uint32_t l0 = __float_as_uint(p0.x - __uint_as_float(a0)), l1 = __float_as_uint(p1.x - __uint_as_float(a1));
+    const uint32_t l2 = __float_as_uint(p0.y - __uint_as_float(a2)), l3 = __float_as_uint(p1.y - __uint_as_float(a3));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mma_tf32_acc(acc[j], a0, a1, a2, a3, __float_as_uint(bcur[j].x), __float_as_uint(bcur[j].y));
+      mma_tf32_acc(acc[j], l0, l1, l2, l3, __float_as_uint(bcur[j].x), __float_as_uint(bcur[j].y));
+      mma_tf32_acc(acc[j], a0, a1, a2, a3, __float_as_uint(bcur[j].z), __float_as_uint(bcur[j].w));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bcur[j] = bnext[j];
   }
-  const int col0 = n0 + tx * 4;
-  const float4 bias = __ldg(reinterpret_cast<const float4*>(head_b + col0));        // head_b is zero padded to ld_head
-  const float bj[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = row0 + ty * 4 + i;
-    if (row >= B) continue;
+  for (int j = 0; j < 8; ++j) {
+    const int col = ct * 64 + j * 8 + 2 * tig;
+    const float b0 = __ldg(head_b + col), b1 = __ldg(head_b + col + 1);          // head_b is zero padded to the padded width
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (col0 + j < outputdim) probs[(size_t)row * outputdim + col0 + j] = 1.f / (1.f + expf(-(acc[i][j] + bj[j])));
+    for (int h = 0; h < 2; ++h) {
+      const int row = row0 + gid + 8 * h;
+      if (row >= B) continue;
+      if (col < outputdim) probs[(size_t)row * outputdim + col] = 1.f / (1.f + expf(-(acc[j][2 * h] + b0)));
+      if (col + 1 < outputdim) probs[(size_t)row * outputdim + col + 1] = 1.f / (1.f + expf(-(acc[j][2 * h + 1] + b1)));
+    }
   }
 }
 }  // namespace
@@ -667,12 +677,9 @@ int launch_head_pooled(const float* pooled, int64_t B, int crops, const float* W
                        int eval_max, float* probs, cudaStream_t s, const uint32_t* c_true, const uint32_t* c_used,
                        const uint32_t* c_min) {
   if (crops == 1 && B < (1ll << 31) - 256) {
-    // single crop: one tiled fp32 GEMM [B,128] x [128,outputdim] with the head LayerNorm as prologue and the sigmoid as
-    // epilogue (every weight tile fetched from L2 feeds 128 clips)
-    const int smem = (kHM * kHLd + 128 * kHN) * (int)sizeof(float);        // 66.5 KB
-    UITK_CHECK_CUDA(cudaFuncSetAttribute(head_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    head_gemm_kernel<<<dim3((unsigned)((B + kHM - 1) / kHM), (unsigned)((outputdim + kHN - 1) / kHN)), 256, smem, s>>>(
-        pooled, (int)B, W + lay.hln_w, W + lay.hln_b, W + lay.head_wt, W + lay.head_b, outputdim, lay.outputdim_padded, probs,
+    // single crop: one tiled GEMM [B,128] x [128,outputdim] with the head LayerNorm as prologue and the sigmoid as epilogue
+    head_tc_kernel<<<dim3((unsigned)((B + 63) / 64), (unsigned)((outputdim + 63) / 64)), 128, 0, s>>>(
+        pooled, (int)B, W + lay.hln_w, W + lay.hln_b, reinterpret_cast<const float4*>(W + lay.head_frag), W + lay.head_b, outputdim, probs,
         c_true, c_used, c_min);
     count_launches(1);
     UITK_CHECK_CUDA(cudaGetLastError());

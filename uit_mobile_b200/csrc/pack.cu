@@ -48,6 +48,7 @@ EncoderLayout make_encoder_layout(const uitk_encoder_cfg& cfg) {
   l.cls_row = take(cur, 128);
   l.ident_scale = take(cur, 64); l.ident_shift = take(cur, 64);
   l.head_wt = take(cur, (size_t)128 * l.outputdim_padded); l.head_b = take(cur, l.outputdim_padded);
+  l.head_frag = take(cur, (size_t)128 * l.outputdim_padded * 2);
   l.blocks = cur;
   size_t b = 0;
   l.blk.ln1_w = take(b, 128); l.blk.ln1_b = take(b, 128);
@@ -321,6 +322,21 @@ int uitk_pack_encoder(const uitk_encoder_cfg* cfg, const float* const* t, void* 
   memcpy(W + l.hln_w, t[10], 128 * sizeof(float)); memcpy(W + l.hln_b, t[11], 128 * sizeof(float));
   transpose_into(W + l.head_wt, t[12], cfg->outputdim, 128, l.outputdim_padded);
   memcpy(W + l.head_b, t[13], cfg->outputdim * sizeof(float));
+  {  // tensor-core head (head_tc_kernel): B fragments of Wt[k][n], tf32 hi + lo (the tensor core ignores the low 13 mantissa bits).
+     // Lane (gid = lane / 4, tig = lane % 4) of k-step s, n-tile j, column tile ct holds k = 8s + 2 tig (+1), n = 64 ct + 8 j + gid.
+    auto trunc = [](float f) { uint32_t u; memcpy(&u, &f, 4); u &= 0xffffe000u; memcpy(&f, &u, 4); return f; };
+    float* F = W + l.head_frag;
+    const float* Wt = W + l.head_wt;
+    for (int ct = 0; ct < l.outputdim_padded / 64; ++ct)
+      for (int s = 0; s < 16; ++s)
+        for (int j = 0; j < 8; ++j)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int k = 8 * s + 2 * (lane & 3), n = 64 * ct + 8 * j + (lane >> 2);
+            const float w0 = Wt[(size_t)k * l.outputdim_padded + n], w1 = Wt[(size_t)(k + 1) * l.outputdim_padded + n];
+            float* f = F + ((((size_t)ct * 16 + s) * 8 + j) * 32 + lane) * 4;
+            f[0] = trunc(w0); f[1] = trunc(w1); f[2] = trunc(w0 - f[0]); f[3] = trunc(w1 - f[1]);
+          }
+  }
   for (int c = 0; c < 128; ++c) W[l.cls_row + c] = t[14][c] + t[15][c];      // cls_token + token_pos_embed (uit.py:390-391)
   for (int m = 0; m < 64; ++m) { W[l.ident_scale + m] = 1.f; W[l.ident_shift + m] = 0.f; }
   for (int i = 0; i < cfg->depth; ++i) {

@@ -91,6 +91,7 @@ struct EncoderLayout {
   size_t cls_row;                     // [128] cls_token + token_pos_embed (pooling='token', uit.py:389-392)
   size_t ident_scale, ident_shift;    // [64] ones / zeros: "input already normalised" (uitk_forward_features)
   size_t head_wt, head_b;             // [128][outputdim_padded], [outputdim_padded]
+  size_t head_frag;                   // head weight as mma.m16n8k8 tf32 B fragments, hi + lo: [outputdim_padded / 64][16 k-steps][8 n-tiles][32 lanes] float4
   int outputdim_padded;
   size_t blocks;                      // first block
   size_t block_stride;

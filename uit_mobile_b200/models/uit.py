@@ -421,7 +421,7 @@ class UITBase(nn.Module):
             raise N.UitkError(f"{what}: UiT hot path runs on CUDA only (no CPU fallback); move the model and input to a B200")
 
     def encode(self, db: torch.Tensor, max_pow: torch.Tensor, out: Optional[torch.Tensor] = None, *,
-               fixup: Optional[tuple] = None, workspace_out: Optional[list] = None) -> torch.Tensor:
+               fixup: Optional[tuple] = None, workspace_out: Optional[list] = None, _blob: Optional[torch.Tensor] = None) -> torch.Tensor:
         """init_bn + crops + forward_features + forward_head on un-clamped log-mel (uit.py:460-492).
 
         ``fixup=(max_used, min_pow)`` turns the call into the device-conditional exact re-run of a speculative encode
@@ -436,7 +436,7 @@ class UITBase(nn.Module):
         l = N.lib()
         B, _, T = db.shape
         cfg = self._cfg()
-        blob = self._encoder_blob(db.device)
+        blob = _blob if _blob is not None else self._encoder_blob(db.device)
         if out is None:
             probs = torch.empty((B, self.outputdim), dtype=torch.float32, device=db.device)
         else:
@@ -546,13 +546,21 @@ class UITBase(nn.Module):
         # maximum while the all-reduce(MAX) of [max, -1 - min] (non-negative floats order like their int32 bit patterns) runs on
         # the NCCL stream, then launch the device-conditional exact re-run: its kernels return at once unless this rank's
         # cutoff was below the global one AND one of its values lies under the global cutoff (uitk_encoder_fixup).
-        g = torch.stack((words[0], -1 - words[1]))
+        g = torch.bitwise_xor(words, self._words_mask(db.device))      # [max, ~min] = [max, -1 - min]: ONE MAX all-reduce for both
         work = dist.all_reduce(g, op=dist.ReduceOp.MAX, group=self.process_group, async_op=True)
-        probs = self.encode(db, max_w, out=out) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
+        blob = self._encoder_blob(db.device) if db.shape[0] else None
+        probs = self.encode(db, max_w, out=out, _blob=blob) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
         work.wait()
         if db.shape[0]:
-            self.encode(db, g[0:1], out=probs, fixup=(max_w, min_w))
+            self.encode(db, g[0:1], out=probs, fixup=(max_w, min_w), _blob=blob)
         return probs
+
+    def _words_mask(self, device) -> torch.Tensor:
+        cache = self.__dict__.setdefault("_words_mask_cache", {})
+        device = torch.device(device)
+        if device not in cache:
+            cache[device] = torch.tensor([0, -1], dtype=torch.int32, device=device)
+        return cache[device]
 
     def _new_words(self, device) -> torch.Tensor:
         """[max power bits = 0, min power bits = +inf] on ``device``: a device-side clone of a cached constant (building the

@@ -74,3 +74,58 @@ def sharded_forward(model, wav_local: torch.Tensor, total: int, group=None, gath
     model.process_group = group if group is not None else dist.group.WORLD
     local = model(wav_local)
     return gather_scores(local, total, group, align) if gather else local
+
+
+class PeerGather:
+    """All-gather of the per-rank score blocks through NVLink peer memory, moved by the COPY ENGINES.
+
+    NCCL's all-gather runs CTAs on the SMs and was measured to slow the log-mel kernel of the next step by 9 % at 8 GPUs; here
+    every rank publishes its block in a symmetric-memory buffer (torch.distributed._symmetric_memory: CUDA IPC / fabric handles
+    exchanged once) and PULLS the peers' blocks with plain device-to-device copies on a side stream - no SM is taken from the
+    kernels of the following batch.  Two tiny barrier kernels (signal pads in the same symmetric allocation) frame the copies:
+    "all blocks published" and "all ranks have read" (the slot may be overwritten again).
+
+        g = PeerGather(sizes, cols, group, device)       # sizes[r] = rows of rank r (sharding.shard_bounds)
+        out, done = g(local)                              # out [sum(sizes), cols]; `done` is recorded when it is complete
+        torch.cuda.current_stream().wait_event(done)      # out stays valid until `depth` more gathers
+
+    Raises if the group cannot map peer memory (no NVLink / IPC): callers fall back to ``gather_scores`` (NCCL)."""
+
+    def __init__(self, sizes: List[int], cols: int, group=None, device=None, depth: int = 2):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if len(sizes) != self.world:
+            raise ValueError("one size per rank")
+        self.sizes, self.cols, self.depth = list(sizes), cols, depth
+        self.offsets = [sum(sizes[:r]) for r in range(self.world)]
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        cap = max(max(sizes), 1)
+        self.src = symm.empty((depth, cap, cols), dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.src, group)
+        self.peer_src = [self.hdl.get_buffer(r, (depth, cap, cols), torch.float32) for r in range(self.world)]
+        self.out = [torch.empty((sum(sizes), cols), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(self.device)
+        self.n = 0
+
+    @torch.no_grad()
+    def __call__(self, local: torch.Tensor):
+        if tuple(local.shape) != (self.sizes[self.rank], self.cols) or local.dtype != torch.float32:
+            raise ValueError(f"rank {self.rank} must pass a float32 [{self.sizes[self.rank]}, {self.cols}] block")
+        slot = self.n % self.depth
+        self.n += 1
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))       # `local` was produced on the caller's stream
+        local.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            self.src[slot, : local.shape[0]].copy_(local, non_blocking=True)
+            self.hdl.barrier(channel=0)                                       # every rank's block is published
+            out = self.out[slot]
+            for step in range(self.world):
+                r = (self.rank - step) % self.world                           # every rank starts at a different peer
+                n = self.sizes[r]
+                if n:
+                    out[self.offsets[r]: self.offsets[r] + n].copy_(self.peer_src[r][slot, :n], non_blocking=True)
+            self.hdl.barrier(channel=1)                                       # every rank has read: the slot may be reused
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return out, done
