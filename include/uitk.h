@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 210
+#define UITK_VERSION 220
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
@@ -183,6 +183,22 @@ UITK_API int uitk_forward_features(const uitk_encoder_cfg* cfg, const void* d_en
                           float* d_tokens, void* d_workspace, size_t workspace_bytes, void* stream);
 UITK_API int uitk_forward_head(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_tokens, int64_t B,
                       int n_tokens, float* d_probs, void* stream);
+
+/* ---- MobileNetV2 (models/mobilenetv2.py:66-178; the reference's distillation teacher / audio-tagging baseline) ------------
+ * Eval forward of the default configuration (inverted_residual_setting of mobilenetv2.py:106-116, width_mult 1.0,
+ * last_channel 1280): conv3x3/2 + BN + ReLU6, 17 inverted-residual blocks, conv1x1 + BN + ReLU6, mean over the mel axis,
+ * Linear(1280 -> outputdim) per time step, sigmoid, mean over time.  fp32 CUDA-core kernels, eval BatchNorm folded at pack time.
+ *   h_tensors   uitk_mnv2_num_tensors() host pointers in the order of uitk_mnv2_tensor_name(i) (state_dict keys)
+ *   d_db        [B, 64, T] log-mel dB AFTER the top-dB clamp (uitk_logmel + uitk_clamp_db = the model's front_end)
+ *   d_probs     [B, outputdim]
+ *   workspace   uitk_mnv2_workspace_bytes(B, T) bytes, 256-B aligned (three activation buffers of <= 256 clips) */
+UITK_API int uitk_mnv2_num_tensors(void);
+UITK_API const char* uitk_mnv2_tensor_name(int index);
+UITK_API size_t uitk_mnv2_blob_bytes(int outputdim);
+UITK_API int uitk_pack_mnv2(int outputdim, const float* const* h_tensors, void* h_blob, size_t blob_bytes);
+UITK_API size_t uitk_mnv2_workspace_bytes(int64_t B, int64_t T);
+UITK_API int uitk_mnv2_forward(int outputdim, const void* d_blob, const float* d_db, int64_t B, int64_t T, float* d_probs,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Debug/validation taps (tests only): copy of the token activations [B*crops*tokens, 128] after patch embed
  * (stage 0) or after block i (stage i+1) is left in the workspace at this byte offset after uitk_encoder. */

@@ -108,6 +108,52 @@ def make_state_dict(arch: str, kind: str = "trained", seed: int = 1, outputdim: 
     return sd
 
 
+def make_mnv2_state_dict(kind: str = "trained", seed: int = 3, outputdim: int = OUTPUTDIM) -> Dict[str, torch.Tensor]:
+    """A full MobileNetV2 state_dict (keys / shapes of the reference's module tree, mobilenetv2.py:118-161), seeded.
+    He-scaled convolutions keep the activations O(1) through the 53 layers; 'trained' adds non-trivial BatchNorm statistics and
+    the sparse-activation classifier of ``make_state_dict``."""
+    from oracle import uit_oracle as O
+    from oracle.mobilenetv2_oracle import SETTING
+    g = np.random.Generator(np.random.PCG64([seed, 0 if kind == "init" else 1, 22]))
+    tr = kind == "trained"
+    sd: Dict[str, torch.Tensor] = {"front_end.0.spectrogram.window": O.hann_window(), "front_end.0.mel_scale.fb": O.melscale_fbanks_htk()}
+
+    def unit(conv, bn, cout, cin_g, k, gain=2.0):
+        fan_in = cin_g * k * k
+        sd[conv + ".weight"] = _t(g.standard_normal((cout, cin_g, k, k)) * np.sqrt(gain / fan_in))
+        sd[bn + ".weight"] = _t(1.0 + g.standard_normal(cout) * (0.1 if tr else 0.0))
+        sd[bn + ".bias"] = _t(g.standard_normal(cout) * (0.1 if tr else 0.0))
+        sd[bn + ".running_mean"] = _t(g.standard_normal(cout) * (0.2 if tr else 0.0))
+        sd[bn + ".running_var"] = _t(g.uniform(0.5, 1.5, cout)) if tr else torch.ones(cout)
+        sd[bn + ".num_batches_tracked"] = torch.tensor(77 if tr else 0, dtype=torch.int64)
+
+    unit("features.0.0", "features.0.1", 32, 1, 3, gain=0.002)      # the input is log-mel dB (tens of dB): scale it to O(1)
+    f, inp = 1, 32
+    for t, c, n, s in SETTING:
+        for i in range(n):
+            p, hidden = f"features.{f}.conv", inp * t
+            j = 0
+            if t != 1:
+                unit(f"{p}.0.0", f"{p}.0.1", hidden, inp, 1); j = 1
+            unit(f"{p}.{j}.0", f"{p}.{j}.1", hidden, 1, 3)
+            unit(f"{p}.{j + 1}", f"{p}.{j + 2}", c, hidden, 1, gain=1.0)
+            inp, f = c, f + 1
+    unit(f"features.{f}.0", f"features.{f}.1", 1280, inp, 1)
+    if tr:
+        n_act = max(5, (40 * outputdim) // 537)
+        scale = np.full((outputdim, 1), 0.01)
+        bias = np.full(outputdim, -6.0)
+        act = g.permutation(outputdim)[:n_act]
+        scale[act] = 0.05
+        bias[act] = -4.0
+        sd["classifier.1.weight"] = _t(g.standard_normal((outputdim, 1280)) * scale)
+        sd["classifier.1.bias"] = _t(bias + g.standard_normal(outputdim) * 0.3)
+    else:
+        sd["classifier.1.weight"] = _t(g.standard_normal((outputdim, 1280)) * 0.01)
+        sd["classifier.1.bias"] = torch.zeros(outputdim)
+    return sd
+
+
 def build_variant(models_pkg, name: str, **kw):
     """Construct VARIANTS[name] from a ``models`` package (the reference's or uit_mobile_b200's: same factories / kwargs)."""
     import torch.nn as nn

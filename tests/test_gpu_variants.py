@@ -172,3 +172,37 @@ def test_encode_validates_its_arguments():
             m.encode(db, mp)
     finally:
         m.eval()
+
+
+@pytest.mark.parametrize("kind", ["init", "trained"])
+def test_mobilenetv2_vs_reference_golden(kind):
+    """models.MobileNetV2 (the reference's teacher, mobilenetv2.py:66-178) on the fp32 CUDA kernels against the reference's own
+    outputs (tests/golden/mobilenetv2.npz): 1 s / short / 1.01 s / 10 s clips and the adversarial batch (batch-global top-dB
+    clamp).  53 fp32 convolution layers with folded BatchNorm: |d prob| <= 5e-5 (measured ~1e-6 on noise; the last feature map agrees
+    to 3.5e-5 of a 0..6 range).  The adversarial batch gets 1e-3: its silent / clamped clips are CONSTANT inputs at the top-dB cutoff, so
+    the front-end's ~1e-4 dB agreement on the batch maximum (test_logmel_q2_batch_global_cutoff) shifts every pixel of those clips
+    the same way.  Literal (tie-aware) top-5 on the sparse 'trained' head."""
+    import uit_mobile_b200 as U
+    m = U.models.MobileNetV2(outputdim=H.OUTPUTDIM)
+    m.load_state_dict(H.make_mnv2_state_dict(kind), strict=True)
+    m = m.to(DEV).eval()
+    g = H.load_golden("mobilenetv2.npz")
+    inputs = {"noise": H.noise_clips(6), "adversarial": H.adversarial_batch(), "short2400": H.noise_clips(3, 2400, seed=11),
+              "len16160": H.noise_clips(2, 16160, seed=14), "long10s": H.noise_clips(2, 160000, seed=13)}
+    for name, x in inputs.items():
+        with torch.no_grad():
+            y = m(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        ref = g[f"{kind}/{name}"]
+        assert y.shape == ref.shape
+        err = float(np.abs(y - ref).max())
+        print(f"  mobilenetv2/{kind}/{name}: max|d prob| = {err:.2e}")
+        assert err <= (1e-3 if name == "adversarial" else 5e-5), (name, err)
+        if kind == "trained" and name in ("noise", "len16160", "long10s"):
+            assert H.tie_aware_topk_equal(ref, y, 5, eps=3e-4), name
+    # a batch larger than the kernel's 256-clip pass, ragged: chunks must not interact (the top-dB scope aside, which is the batch's)
+    xb = torch.from_numpy(H.noise_clips(300, 4000, seed=9)).to(DEV)
+    with torch.no_grad():
+        full = m(xb)
+        db = m.front_end(xb)
+    assert full.shape == (300, H.OUTPUTDIM) and torch.isfinite(full).all()
+    assert tuple(m(torch.zeros(0, 16000, device=DEV)).shape) == (0, H.OUTPUTDIM)

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.uitk_version() == 210
+    assert lib.uitk_version() == 220
 
 
 def test_geometry_helpers_match_oracle(lib):
@@ -290,3 +290,26 @@ def test_no_cpu_fallback():
         m.blocks(torch.zeros(1, 24, 128))
     src = open(os.path.join(H.REPO, "uit_mobile_b200", "models", "uit.py")).read()
     assert "oracle" not in src.replace("no CPU path", "")
+
+
+def test_mobilenetv2_module_contract(lib):
+    from uit_mobile_b200 import _native as N
+    """models.MobileNetV2: the reference's state_dict keys / shapes / dtypes in the reference's order (state_dict_layout_mnv2.txt is
+    the reference's own list), strict loading of a full state_dict, the kernel's tensor order, and loud refusals."""
+    import uit_mobile_b200 as U
+    m = U.models.MobileNetV2(outputdim=537)
+    want = [l.rstrip("\n").split("\t")[1:] for l in open(os.path.join(H.GOLDEN_DIR, "state_dict_layout_mnv2.txt"))]
+    got = [[k, str(tuple(v.shape)), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert got == want
+    m.load_state_dict(H.make_mnv2_state_dict("trained"), strict=True)
+    names = N.mnv2_tensor_names()
+    assert len(names) == lib.uitk_mnv2_num_tensors() == 52 * 5 + 2 and set(names) <= set(m.state_dict())
+    assert names[0] == "features.0.0.weight" and names[-2:] == ["classifier.1.weight", "classifier.1.bias"]
+    assert lib.uitk_mnv2_blob_bytes(537) > 4 * (1280 * 537 + 320 * 1280) and lib.uitk_mnv2_workspace_bytes(4, 101) > 0
+    with pytest.raises(N.UitkError):
+        m.eval()(torch.zeros(2, 16000))                  # CUDA only, no fallback
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros(2, 16000))
+    for kw in (dict(width_mult=0.5), dict(last_channel=640), dict(inverted_residual_setting=[[1, 16, 1, 1]]), dict(n_mels=80)):
+        with pytest.raises(NotImplementedError):
+            U.models.MobileNetV2(**kw)

@@ -119,3 +119,14 @@ def test_sliding_window_premise_interior_frames_are_stream_frames():
     for w in range(mel_w.shape[0]):
         assert torch.equal(mel_w[w][:, 2:99], mel_s[:, w * r + 2: w * r + 99])
     assert not torch.equal(mel_w[1][:, :2], mel_s[:, r: r + 2])          # edge frames are NOT shared
+
+
+def test_mobilenetv2_oracle_vs_reference_golden():
+    """oracle/mobilenetv2_oracle.py against the committed outputs of the reference's own MobileNetV2 (generate_golden_mnv2.py)."""
+    from oracle import mobilenetv2_oracle as M
+    g = H.load_golden("mobilenetv2.npz")
+    for kind in ("init", "trained"):
+        sd = H.make_mnv2_state_dict(kind)
+        for name, x in (("noise", H.noise_clips(6)), ("short2400", H.noise_clips(3, 2400, seed=11))):
+            y = M.forward(sd, torch.from_numpy(x)).numpy()
+            assert np.abs(y - g[f"{kind}/{name}"]).max() <= 5e-6

@@ -70,6 +70,12 @@ SIGNATURES = {
     "uitk_forward_features": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_size_t, C.c_void_p]),
     "uitk_forward_head": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "uitk_mnv2_num_tensors": (C.c_int, []),
+    "uitk_mnv2_tensor_name": (C.c_char_p, [C.c_int]),
+    "uitk_mnv2_blob_bytes": (C.c_size_t, [C.c_int]),
+    "uitk_pack_mnv2": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]),
+    "uitk_mnv2_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "uitk_mnv2_forward": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uitk_encoder_tokens_offset": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64, C.c_int]),
     "uitk_debug_taps": (None, [C.c_int]),
     "uitk_debug_read_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -104,3 +110,8 @@ def check(rc: int, what: str) -> None:
 def encoder_tensor_names(depth: int):
     l = lib()
     return [l.uitk_encoder_tensor_name(depth, i).decode() for i in range(l.uitk_encoder_num_tensors(depth))]
+
+
+def mnv2_tensor_names():
+    l = lib()
+    return [l.uitk_mnv2_tensor_name(i).decode() for i in range(l.uitk_mnv2_num_tensors())]
