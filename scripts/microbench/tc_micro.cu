@@ -8,12 +8,6 @@
 
 using namespace uitk::tc;
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 __global__ void __launch_bounds__(512, 1) micro(long long* out, int nw_ld, int mma_n, int mma_k, int a_tmem) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[4];
@@ -175,6 +169,27 @@ int main() {
     if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
     printf("MMA %s M128 N%3d x %2d k-steps: issue+commit %5lld cyc, round trip (issue -> commit -> mbarrier wake) %5lld cyc\n", ts ? "TS(A in TMEM)" : "SS", n, k, h[3], h[2]);
+  }
+  // ---- the front-end north_star sketches: the 512-point DFT as tcgen05 contractions, factored 16 x 32.  Operands bf16
+  // hi + lo, 3 products per k-step (2^-16 relative; fp32-grade needs hi/mid/lo = 6 products).  Only the MMA issue stream of a
+  // 128-row tile is timed, operands already in SMEM / TMEM - no framing, windowing, twiddles, operand splits, TMEM round trips.
+  //   stage 1: 32 real 16-point DFTs per frame: rows = 4 frames x 32, K = 16 (1 k-step), N = 32        -> 3 k-steps / 4 frames (SS)
+  //   stage 2: 16 complex 32-point DFTs per frame: rows = 8 frames x 16, K = 64 (4 k-steps), N = 64    -> 12 k-steps / 8 frames (TS)
+  {
+    double cyc_frame[2] = {0, 0};
+    for (int prod : {3, 6}) {
+      micro<<<148, 512, 128 * 1024>>>(d, 1, 32, 32 * prod, 0);             // 32 tiles of stage 1 back to back
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
+      cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+      const double s1 = (double)h[2] / (32.0 * 4.0);                         // cycles per frame
+      micro<<<148, 512, 128 * 1024>>>(d, 1, 64, 8 * 4 * prod, 1);           // 8 tiles of stage 2
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
+      cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+      const double s2 = (double)h[2] / (8.0 * 8.0);
+      cyc_frame[prod == 6] = s1 + s2;
+      printf("two-stage tcgen05 DFT, %d products/k-step: stage 1 %.1f + stage 2 %.1f = %.1f tensor-pipe cycles per frame and SM -> %.3f ms for the bench's "
+             "413 696 frames on 148 SMs at 1.965 GHz (MMA issue stream ALONE)\n", prod, s1, s2, s1 + s2, (s1 + s2) * 413696.0 / 148.0 / 1.965e6);
+    }
   }
   printf("st.shared + fence.proxy.async: %lld cyc; mbarrier arrive -> waiter wake: %lld cyc; bar.sync 256 threads: %lld cyc\n", h[4], h[5], h[6]);
   return 0;
