@@ -559,7 +559,10 @@ def run_b200(args):
                             "traffic": ncu_traffic("encoder_tc_kernel", arch, units) if args.precision == "bf16" else None,
                             "traffic_unit": "bytes/launch (dram read+write)",
                             "traffic_source": "committed ncu --set full capture (profiles/traffic.json), not measured in this run",
-                            "peak_source": tsrc, "ms_per_launch": ms_encoder, "ms_per_launch_source": "CUDA events around the launch in the serialised pass",
+                            "peak_source": tsrc, "ms_per_launch": ms_encoder,
+                            "ms_per_launch_source": "CUDA events around the launch in the serialised pass" + (
+                                "; at N > 1 the span also holds the wait for the max-word all-reduce of the slowest rank (ranks are not re-aligned "
+                                "between steps): quote the kernel's roofline from the N = 1 line" if world > 1 else ""),
                             "flops_per_clip": flops, "clips_per_launch": units}
         if kind == "clips":
             fe_gbs = units * LOGMEL_BYTES_1S / (ms_logmel * 1e-3) / 1e9
