@@ -76,6 +76,12 @@ constexpr int kHSlots = 3;                         // hidden-chunk slots (16 KB 
 constexpr uint32_t kColP = 0, kColO = 64;
 // MLP phase: fc1 chunk accumulator (64 fp32 columns) and the LayerNorm-2 output as packed-bf16 TMEM A operand (64 columns)
 constexpr uint32_t kColFc1 = 0, kColLn2 = 64;
+// Patch embed: operand slot 2 is idle (the patch operand half takes slots 0|1), so the producer warp parks the per-token
+// position table there ([24][128] fp32, rows 528 B apart: a quarter warp's 16-byte reads of 8 consecutive token rows then
+// hit 8 distinct bank groups).  Read by every compute thread once per tile, before block 0 writes V^T over it.
+constexpr uint32_t OFF_POS = 2 * 16384;
+constexpr uint32_t kPosRow = 132;                  // floats per staged table row
+static_assert(24 * kPosRow * 4 <= 16384, "position table must fit operand slot 2");
 constexpr uint32_t OFF_RING = kHSlots * 16384;
 // constant MMA operands: k-group of (1, 1, 1, 0, ..) rows = the A operand of every bias k-step, then 2 KB of zeros that
 // serve as the second k-group of both the ones operand and every bias tile (their LBO points here: it must lie ABOVE the ring)
@@ -86,7 +92,7 @@ constexpr uint32_t kSmemBytes = OFF_BAR + 256;
 static_assert(kSmemBytes <= 115712, "two CTAs per SM need <= 113 KB of dynamic shared memory each");
 constexpr uint32_t kTmemCols = 256;
 
-enum { B_FULLW = 0, B_EMPTYW = kSlots, B_ACC = 2 * kSlots, B_X, B_FC1, B_H /* kHSlots hidden slots */, B_COUNT = B_H + kHSlots };
+enum { B_FULLW = 0, B_EMPTYW = kSlots, B_ACC = 2 * kSlots, B_X, B_FC1, B_POS, B_H /* kHSlots hidden slots */, B_COUNT = B_H + kHSlots };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct TcParams {
@@ -242,6 +248,61 @@ __device__ __forceinline__ uint4 relu_pack8(const float* v) {
   return o;
 }
 
+// Patch gather of one K half: clamp(dB) * BatchNorm scale + shift -> bf16, written straight into the K-major operand tile.
+// tokens == 24 (t_n == 6: 96 frames = 3 x 32 lanes, no tail predicate).  Element (mel row u, frame tt = lane + 32 j):
+// k = (dfl0 + u) * 16 + (lane & 15), row = g * 24 + f * 6 + 2 j + (lane >> 4)  ->  shared offset = per-lane base
+// + u * 4096 + j * 32 + g * 384 with compile-time u, j terms: the stores need no address arithmetic.
+// The gather is bound by the round-trip latency of its loads (~1.5 k cycles each in the stage timeline), not by their count,
+// so ALL (up to 5) clip-crops of the tile are loaded at once: 60 loads in flight per lane.  Deliberately NOT inlined: inside the
+// megakernel the persistent state of the tile loop leaves room for a dozen loads only (ptxas spilled every load result to
+// local memory, which serialises them); as a call, the state is saved once around it and the 60 values stay in registers.
+template <bool kMasked>
+__device__ __noinline__ void gather_half(const float* __restrict__ db, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                         unsigned char* A, int T, int crops, int target, int rr0, int g_cnt, int half, int warp, int lane,
+                                         int t_n, float cutoff, uint64_t* wait_bar, uint32_t wait_parity) {
+  const int f = warp >> 1, dfl0 = 4 * (warp & 1);
+  const int mel0 = 16 * f + 8 * half + dfl0;
+  unsigned char* lane_dst = A + (2 * dfl0 + ((lane & 15) >> 3)) * 2048 + (f * 6 + (lane >> 4)) * 16 + (lane & 7) * 2;
+  float val[5][4][3];
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    {
+      const int rr = rr0 + min(g, g_cnt - 1);          // a ragged last tile re-loads its last clip-crop (never stored)
+      int b = rr, start = 0;
+      if (crops > 1) {
+        b = rr / crops;
+        start = (rr - b * crops) * target;
+        if (start > T - target) start = T - target;
+      }
+      const float* src = db + ((size_t)b * 64 + mel0) * T + start + lane;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) val[g][u][j] = (!kMasked || lane + 32 * j < 16 * t_n) ? __ldg(src + 32 * j) : 0.f;
+        src += T;
+      }
+    }
+  }
+  float sc[4], sh[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { sc[u] = __ldg(bn_scale + mel0 + u); sh[u] = __ldg(bn_shift + mel0 + u); }
+  if (wait_bar != nullptr) mbar_wait_all(wait_bar, wait_parity);       // the operand tile is free (loads already in flight)
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g < g_cnt) {
+      unsigned char* d = lane_dst + g * (24 * 16);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float y = fmaf(fmaxf(val[g][u][j], cutoff), sc[u], sh[u]);
+          *reinterpret_cast<__nv_bfloat16*>(d + u * 4096 + j * 32) =
+              __float2bfloat16_rn((!kMasked || lane + 32 * j < 16 * t_n) ? y : 0.f);       // masked slots: zero patch
+        }
+    }
+  }
+}
+
 // kMasked = false: the native geometry (1 s clips: 6 time patches, all 24 token slots live).
 // kMasked = true : clips of 2400 .. 15 359 samples (1 .. 5 time patches).  The tile keeps the 24-slot layout (slot = band * 6 +
 //   tau) so that every offset, the position table and the 5-clips-per-tile packing stay as they are; slots with tau >= t_n
@@ -306,7 +367,19 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
         }
         __syncwarp();
         const unsigned char* wb = p.wts;
-        for (int c = 0; c < 4; ++c) ring_load(wb, kTile);
+        for (int c = 0; c < 4; ++c) {
+          ring_load(wb, kTile);
+          if (c == 2) {
+            // Patch quarter 2 re-uses the ring slot of the previous tile's last fc2 chunk: its "empty" barrier has just
+            // completed, so every MMA of that tile is done and nothing reads operand slot 2 any more (the pooling stage
+            // only uses slots 0|1).  Stage the position table there, one 512-byte row at a time.
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars[B_POS], 24 * 512);
+              for (int t = 0; t < 24; ++t) bulk_g2s(smem + OFF_POS + t * (kPosRow * 4), p.pos_tab + t * 128, 512, &bars[B_POS]);
+            }
+            __syncwarp();
+          }
+        }
         for (int blk = 0; blk < p.depth; ++blk) {                 // same order as the MMA issuer consumes (pack.cu)
           ring_load(wb, kQkvHalfBytes + kQkvBiasBytes);
           ring_load(wb, kQkvHalfBytes);
@@ -461,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
     const int r = q * 32 + lane;                                   // row == TMEM lane
     const uint32_t tx = tmem + ((uint32_t)(q * 32) << 16);         // X columns 0..127
     const uint32_t tacc = tx + 128;                                // accumulator columns 128..255
-    uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0;      // ph_h: one phase bit per hidden slot
+    uint32_t ph_acc = 0, ph_x = 0, ph_fc1 = 0, ph_h = 0, ph_pos = 0;      // ph_h: one phase bit per hidden slot
     uint32_t sig = 0;                     // "operand ready" signal counter (mirrors the issuer's)
 #ifdef UITK_TRACE
     const bool trace_on = blockIdx.x == 0 && tid == 0;
@@ -496,56 +569,27 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
       // ---------------- patch embed: gather (clamp + BatchNorm) -> bf16 A, one K half [128 x 128] at a time ----------------
       // k = df * 16 + dt (df = mel & 15): K half h holds df in [8h, 8h + 8).  Warp w gathers token row f = w >> 1 and the
       // 4 mel rows 16 f + 8 h + 4 (w & 1) + u of every clip-crop of the tile (12 coalesced loads in flight per lane).
+      for (int i = tid; i < (128 - rows_valid) * 16; i += kCompute) {        // zero the padding rows (both K halves use the same bytes)
+        const int rz = rows_valid + i / 16, k8 = i % 16;
+        *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        if (half == 1) {                                                   // MMAs of half 0 have read A
-          mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
-        }
-        for (int i = tid; i < (128 - rows_valid) * 16; i += kCompute) {      // zero the padding rows
-          const int rz = rows_valid + i / 16, k8 = i % 16;
-          *reinterpret_cast<uint4*>(smem + OFF_A + k8 * 2048 + rz * 16) = make_uint4(0, 0, 0, 0);
-        }
-        // tokens == 24 (t_n == 6: 96 frames = 3 x 32 lanes, no tail predicate).  Element (mel row u, frame tt = lane + 32 j):
-        // k = (dfl0 + u) * 16 + (lane & 15), row = g * 24 + f * 6 + 2 j + (lane >> 4)  ->  shared offset = per-lane base
-        // + u * 4096 + j * 32 + g * 384 with compile-time u, j terms: the stores need no address arithmetic.
-        const int f = warp >> 1, dfl0 = 4 * (warp & 1);
-        const int mel0 = 16 * f + 8 * half + dfl0;
-        unsigned char* lane_dst = smem + OFF_A + (2 * dfl0 + ((lane & 15) >> 3)) * 2048 + (f * 6 + (lane >> 4)) * 16 + (lane & 7) * 2;
-        float sc[4], sh[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { sc[u] = __ldg(p.bn_scale + mel0 + u); sh[u] = __ldg(p.bn_shift + mel0 + u); }
-#pragma unroll 1
-        for (int g = 0; g < g_cnt; ++g) {
-          const int rr = rr0 + g;
-          const int b = rr / p.crops, c = rr - b * p.crops;
-          int start = 0;
-          if (p.crops > 1) { start = c * p.target; if (start > p.T - p.target) start = p.T - p.target; }
-          const float* src = p.db + ((size_t)b * 64 + mel0) * p.T + start + lane;
-          float val[4][3];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) val[u][j] = (!kMasked || lane + 32 * j < 16 * t_n) ? __ldg(src + 32 * j) : 0.f;
-            src += p.T;
-          }
-          unsigned char* d = lane_dst + g * (24 * 16);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float y = fmaf(fmaxf(val[u][j], cutoff), sc[u], sh[u]);
-              *reinterpret_cast<__nv_bfloat16*>(d + u * 4096 + j * 32) =
-                  __float2bfloat16_rn((!kMasked || lane + 32 * j < 16 * t_n) ? y : 0.f);       // masked slots: zero patch
-            }
-        }
+        // half 1: its loads are issued first, THEN the wait for the MMAs of half 0 (which still read A), then the stores
+        gather_half<kMasked>(p.db, p.bn_scale, p.bn_shift, smem + OFF_A, p.T, p.crops, p.target, rr0, g_cnt, half, warp, lane, t_n, cutoff,
+                             half == 1 ? &bars[B_ACC] : nullptr, ph_acc);
+        if (half == 1) ph_acc ^= 1;
         signal_ready();
       }
       TR(0, 2);
       mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;
       tc_fence_after();
       TR(0, 3);
-      {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383; one pre-added table row per token), back to TMEM
-        const float* pt = p.pos_tab + (r % tokens) * 128;
+      {   // x += conv bias + time_pos[tau] + freq_pos[f]   (uit.py:380-383; one pre-added table row per token), back to TMEM.
+          // The table row comes from the staged copy in operand slot 2 (thread == row: from global memory these were 32
+          // different cache lines per warp load, ~6.8 k cycles per tile).
+        mbar_wait_all(&bars[B_POS], ph_pos); ph_pos ^= 1;
+        const float* pt = reinterpret_cast<const float*>(smem + OFF_POS) + (r % tokens) * kPosRow;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float v[32];
@@ -555,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           if (r < rows_valid) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 pb = __ldg(reinterpret_cast<const float4*>(pt + c0 + i));
+              const float4 pb = *reinterpret_cast<const float4*>(pt + c0 + i);
               v[i] += pb.x; v[i + 1] += pb.y; v[i + 2] += pb.z; v[i + 3] += pb.w;
             }
           }
