@@ -36,14 +36,49 @@ def main():
     model = getattr(U.models, arch)(outputdim=537, target_length=102).to("cuda:0").eval()
     x = (0.1 * torch.randn(batch, 16000, device="cuda:0")).clamp_(-1, 1)
     with torch.no_grad():
-        for _ in range(3):
+        for _ in range(int(os.environ.get("TRACE_WARM", 3))):
             model(x)
     torch.cuda.synchronize()
     out = []
+    # event-timed duration of the two halves of forward() in this (trace) build, for comparison with the cycle stamps
+    fe = model.front_end
+    with torch.no_grad():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_fe = t_enc = 0.0
+        for _ in range(10):
+            words = fe.new_words(x.device)
+            e[0].record()
+            db, _ = fe.logmel_unclamped(x, max_pow=words[0:1], min_pow=words[1:2])
+            e[1].record()
+            model.encode(db, words[0:1])
+            e[2].record()
+            torch.cuda.synchronize()
+            t_fe += e[0].elapsed_time(e[1]); t_enc += e[1].elapsed_time(e[2])
+        out.append(f"== event-timed (trace build): front-end {t_fe / 10:.4f} ms, encoder+head {t_enc / 10:.4f} ms")
+        for _ in range(int(os.environ.get("TRACE_WARM", 3))):
+            model(x)
+        torch.cuda.synchronize()
+    cta = np.zeros(4096, dtype=np.int64)
+    N.check(lib.uitk_debug_read_trace(cta.ctypes.data, 2, 4096), "read_trace")
+    cta = cta.reshape(1024, 4)
+    cta = cta[cta[:, 0] > 0]
+    t0 = cta[:, 0].min()
+    st, en = (cta[:, 0] - t0) / 1e3, (cta[:, 1] - t0) / 1e3
+    out.append(f"== per-CTA lifetimes (globaltimer, us): {len(cta)} CTAs; start min/median/max {st.min():.1f}/{np.median(st):.1f}/{st.max():.1f}; "
+               f"end min/median/max {en.min():.1f}/{np.median(en):.1f}/{en.max():.1f}; CTA 0: {st[0]:.1f} .. {en[0]:.1f}")
+    mhz = cta[:, 3] / (cta[:, 1] - cta[:, 0]) * 1e3
+    out.append(f"   effective SM clock over a CTA's life (cycles / globaltimer): median {np.median(mhz):.0f} MHz, min {mhz.min():.0f}, max {mhz.max():.0f}")
+    order = np.argsort(en)
+    out.append("   latest CTAs (idx, sm, start, end): " + "  ".join(f"({i},{cta[i, 2]},{st[i]:.0f},{en[i]:.0f})" for i in order[-6:]))
+    sm_count = np.bincount(cta[:, 2].astype(int))
+    out.append(f"   CTAs per SM: min {sm_count[sm_count > 0].min()} max {sm_count.max()} (SMs used {np.count_nonzero(sm_count)})")
     for which, names in ((0, NAMES), (1, INAMES)):
         buf = np.zeros(4096, dtype=np.int64)
         N.check(lib.uitk_debug_read_trace(buf.ctypes.data, which, 4096), "read_trace")
         ids, clk = decode(buf)
+        if len(ids) < 2:
+            out.append(f"== {'compute thread 0' if which == 0 else 'MMA issuer'}: no stamps (UITK_TRACE=2 build)")
+            continue
         out.append(f"== {'compute thread 0' if which == 0 else 'MMA issuer'}: {len(ids)} stamps, total {clk[-1] - clk[0]} cycles")
         d = np.diff(clk)
         agg = defaultdict(list)

@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     flags = list(FLAGS)
     if os.environ.get("UITK_TRACE"):        # in-kernel stage timeline of the tensor-core encoder (profiling builds only)
-        flags.append("-DUITK_TRACE")
+        flags.append("-DUITK_TRACE=" + os.environ["UITK_TRACE"])
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []

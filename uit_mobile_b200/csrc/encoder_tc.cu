@@ -31,6 +31,7 @@
 // Measured design inputs (scripts/microbench/tc_micro.cu, profiles/r1_tc_microbench.txt): SS k-step = max(~39, N/2)
 // cycles, TS k-step = max(~11, N/2); fence.proxy.async ~120-140; mbarrier wake ~140-150; named barrier ~30.
 // Reference semantics: models/uit.py:379-396 (features), 89-122 (attention), 181-248 (MLP, block).
+#include <cstdlib>
 #include <type_traits>
 
 #include "tc_ptx.cuh"
@@ -111,9 +112,14 @@ struct TcParams {
 
 // Optional in-kernel timeline (build with -DUITK_TRACE): thread 0 of CTA 0 and its MMA-issuer thread stamp
 // (id << 44 | clock) at every stage boundary; read back with uitk_debug_read_trace.  Compiled out by default.
+// CAUTION when reading it: the stamps themselves cost the MMA-issuer warp ~10 % per block (it is the busiest warp), so
+// stage SHARES are meaningful, absolute block times are not - decide between kernel variants with the normal build.
 #ifdef UITK_TRACE
-__device__ long long g_trace[2][4096];
-#define TR(buf, id) do { if (trace_on && tr_n < 4096) g_trace[buf][tr_n++] = ((long long)(id) << 44) | (clock64() & ((1ll << 44) - 1)); } while (0)
+__device__ long long g_trace[3][4096];     // [2]: per CTA (globaltimer at start, at end, SM id, SM cycles start -> end), 4 words each
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+// UITK_TRACE=2: stamps of the compute thread only (the issuer warp runs undisturbed: realistic block times)
+#define TR(buf, id) do { if ((UITK_TRACE < 2 || (buf) == 0) && trace_on && tr_n < 4096) g_trace[buf][tr_n++] = ((long long)(id) << 44) | (clock64() & ((1ll << 44) - 1)); } while (0)
 #else
 #define TR(buf, id) do {} while (0)
 #endif
@@ -312,6 +318,11 @@ template <bool kMasked>
 __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams p) {
   if (p.c_used != nullptr && !fixup_needed(p.max_pow, p.c_used, p.c_min)) return;   // uniform: before any allocation / barrier
   extern __shared__ __align__(1024) unsigned char smem[];
+#ifdef UITK_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {
+    g_trace[2][blockIdx.x * 4] = globaltimer_ns(); g_trace[2][blockIdx.x * 4 + 2] = smid(); g_trace[2][blockIdx.x * 4 + 3] = -clock64();
+  }
+#endif
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
   float* part = reinterpret_cast<float*>(smem + OFF_PART);
@@ -623,29 +634,18 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
           // ---------- tensor-core attention: S_h = Q_h K_h^T and O_h = P_h V_h on tcgen05, softmax straight from TMEM ----------
           const bool valid = r < rows_valid;
           const int g = valid ? r / 24 : 0;
-          {   // qkv (+bias) -> bf16 operands.  hsel 0 holds q(32) k_h0(16); hsel 1 holds k_h1(16) v(32)
+          {   // qkv (+bias) -> bf16 operands.  Accumulator columns: q 0..31 | k 32..63 | v 64..95 (two heads of 16 each).
+              // hsel 0 takes q + v of head 0, hsel 1 takes k + v of head 1: four 16-byte stores and 16 transposing 2-byte stores each
             float v[32], w[16];
-            tmem_ld32(tacc + hsel * 48, v);
-            tmem_ld16(tacc + hsel * 48 + 32, w);
+            tmem_ld32(tacc + hsel * 32, v);
+            tmem_ld16(tacc + 64 + hsel * 16, w);
             tmem_ld_wait();
-            if (hsel == 0) {
+            unsigned char* qk = smem + (hsel == 0 ? OFF_Q : OFF_K) + r * 16;   // Q_h / K_h: head c >> 1 at + 4096, k-group c & 1 at + 2048
 #pragma unroll
-              for (int c = 0; c < 4; ++c)                               // q: head c>>1, k-group c&1
-                *reinterpret_cast<uint4*>(smem + OFF_Q + (c >> 1) * 4096 + (c & 1) * 2048 + r * 16) = pack8_bf16(v + c * 8);
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(qk + (c >> 1) * 4096 + (c & 1) * 2048) = pack8_bf16(v + c * 8);
+            unsigned char* vt = smem + OFF_VT + hsel * kVtHead + (r >> 3) * kVtLbo + (r & 7) * 2;   // V_h^T[d][key r]
 #pragma unroll
-              for (int c = 0; c < 2; ++c)                               // k, head 0
-                *reinterpret_cast<uint4*>(smem + OFF_K + c * 2048 + r * 16) = pack8_bf16(w + c * 8);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 2; ++c)                               // k, head 1
-                *reinterpret_cast<uint4*>(smem + OFF_K + 4096 + c * 2048 + r * 16) = pack8_bf16(v + c * 8);
-              unsigned char* vt = smem + OFF_VT + (r >> 3) * kVtLbo + (r & 7) * 2;   // V^T[d][key r]
-#pragma unroll
-              for (int d = 0; d < 16; ++d) {
-                *reinterpret_cast<__nv_bfloat16*>(vt + d * 16) = __float2bfloat16_rn(v[16 + d]);            // head 0
-                *reinterpret_cast<__nv_bfloat16*>(vt + kVtHead + d * 16) = __float2bfloat16_rn(w[d]);       // head 1
-              }
-            }
+            for (int d = 0; d < 16; ++d) *reinterpret_cast<__nv_bfloat16*>(vt + d * 16) = __float2bfloat16_rn(w[d]);
           }
           signal_ready();
           TR(0, 13);
@@ -655,47 +655,35 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             mbar_wait_all(&bars[B_ACC], ph_acc); ph_acc ^= 1;            // S_h in ACC
             tc_fence_after();
             TR(0, 14);
-            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp straddle two clips: load the
-            // key window of each of the two clips in turn and let every lane keep the one that belongs to its row
-            float sv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp straddle two clips: load the key
+            // window of BOTH clips (one wait) and let every lane keep the one that belongs to its row.  The two warps of a
+            // row pair split the 24 keys 12 / 12 (hsel 0: keys 0..11, hsel 1: keys 12..23): equal work on both.
             const int g_lo = (q * 32) / 24;                              // clip of the warp's first row (warp-uniform)
+            const bool two = g_lo < 4;                                   // rows 96..127: clip 4 only (the rest is padding)
+            float sv[12];
+            {
+              float t0[12], t1[12];
+              tmem_ld8(tacc + g_lo * 24 + hsel * 12, t0); tmem_ld4(tacc + g_lo * 24 + hsel * 12 + 8, t0 + 8);
+              if (two) { tmem_ld8(tacc + g_lo * 24 + 24 + hsel * 12, t1); tmem_ld4(tacc + g_lo * 24 + 24 + hsel * 12 + 8, t1 + 8); }
+              tmem_ld_wait();
+              const bool first = g == g_lo;
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-              const int gg = g_lo + pass;
-              if (gg <= 4) {
-                float t[16];
-                if (hsel == 0) { tmem_ld8(tacc + gg * 24, t); tmem_ld8(tacc + gg * 24 + 8, t + 8); }
-                else { tmem_ld8(tacc + gg * 24 + 16, t); }
-                tmem_ld_wait();
-                if (valid && g == gg) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) sv[i] = t[i];
-                }
-              }
+              for (int i = 0; i < 12; ++i) sv[i] = valid ? ((first || !two) ? t0[i] : t1[i]) : 0.f;
             }
-            if (kMasked) {   // key slot kc = i (hsel 0) / 16 + i (hsel 1) is live iff its time index kc % 6 < t_n
+            if (kMasked) {   // key slot hsel * 12 + i is live iff its time index i % 6 < t_n (slots 0 and 12 always are)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int tau = hsel == 0 ? i % 6 : (16 + i) % 6;
-                if (tau >= t_n) sv[i] = -INFINITY;                        // every half row keeps a live key (slots 0 and 18)
-              }
+              for (int i = 0; i < 12; ++i)
+                if (i % 6 >= t_n) sv[i] = -INFINITY;
             }
-            // hsel 0 owns keys 0..15 of the clip, hsel 1 keys 16..23 (sv[8..15] unused there); tree reductions for ILP
             float m_loc, l_loc;
             {
-              float m8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) m8[i] = hsel == 0 ? fmaxf(sv[i], sv[i + 8]) : sv[i];
-              m_loc = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+              const float m0 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3])), m1 = fmaxf(fmaxf(sv[4], sv[5]), fmaxf(sv[6], sv[7]));
+              const float m2 = fmaxf(fmaxf(sv[8], sv[9]), fmaxf(sv[10], sv[11]));
+              m_loc = fmaxf(fmaxf(m0, m1), m2);
               const float mb = -m_loc * kScaleLog2e;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sv[i] = (hsel == 0 || i < 8) ? ex2_approx(fmaf(sv[i], kScaleLog2e, mb)) : 0.f;
-              float s8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) s8[i] = sv[i] + sv[i + 8];
-              l_loc = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+              for (int i = 0; i < 12; ++i) sv[i] = ex2_approx(fmaf(sv[i], kScaleLog2e, mb));
+              l_loc = (((sv[0] + sv[1]) + (sv[2] + sv[3])) + ((sv[4] + sv[5]) + (sv[6] + sv[7]))) + ((sv[8] + sv[9]) + (sv[10] + sv[11]));
             }
             float* ex = part + h * 512;
             *reinterpret_cast<float2*>(ex + (hsel * 128 + r) * 2) = make_float2(m_loc, l_loc);
@@ -704,26 +692,29 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
             const float M = fmaxf(m_loc, oth.x);
             const float f_own = ex2_approx((m_loc - M) * kScaleLog2e), f_oth = ex2_approx((oth.x - M) * kScaleLog2e);
             const float f = valid ? __fdividef(f_own, l_loc * f_own + oth.y * f_oth) : 0.f;
+            // P_h -> tensor memory.  Row r holds its clip's 24 probabilities in packed columns [12 g, 12 g + 12) (this thread:
+            // 6 of them, at + 6 hsel) and zeros elsewhere.  tcgen05.st takes one (warp-uniform) column address, so every clip's
+            // column block is stored by the whole warp: in the (at most two) blocks of the warp's own clips the lanes of that
+            // clip store their values and the others zeros; the remaining blocks are all zeros.  All S_h reads of the CTA
+            // happened before the exchange barrier above, so overwriting S_h is safe.
+            uint32_t pk[6];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] *= f;
-            // P_h -> tensor memory.  Row r holds its clip's 24 probabilities in packed columns [12 g, 12 g + 12) and zeros
-            // elsewhere.  tcgen05.st takes one (warp-uniform) column address, so every clip's column block is stored by the
-            // whole warp: lanes of that clip store their values, all other lanes zeros (this thread: 8 of the 12 columns
-            // for hsel 0, the last 4 for hsel 1, which also clears the 4 tail columns).  All S_h reads of the CTA happened
-            // before the exchange barrier above, so overwriting S_h is safe.
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pk[j] = pack2_bf16(sv[2 * j], sv[2 * j + 1]);
+            for (int j = 0; j < 6; ++j) pk[j] = pack2_bf16(sv[2 * j] * f, sv[2 * j + 1] * f);
+            const uint32_t zero6[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-              const bool mine = valid && g == c;
-              uint32_t z[8];
+              const uint32_t col = tacc + kColP + 12 * c + 6 * hsel;
+              if (c == g_lo || c == g_lo + 1) {                           // warp-uniform
+                const bool mine = valid && g == c;
+                uint32_t z[6];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) z[j] = mine ? pk[j] : 0u;
-              if (hsel == 0) { tmem_st4(tacc + kColP + 12 * c, z); tmem_st4(tacc + kColP + 12 * c + 4, z + 4); }
-              else tmem_st4(tacc + kColP + 12 * c + 8, z);
+                for (int j = 0; j < 6; ++j) z[j] = mine ? pk[j] : 0u;
+                tmem_st4(col, z); tmem_st2(col + 4, z + 4);
+              } else {
+                tmem_st4(col, zero6); tmem_st2(col + 4, zero6 + 4);
+              }
             }
-            if (hsel == 1) { const uint32_t z[4] = {0u, 0u, 0u, 0u}; tmem_st4(tacc + kColP + 60, z); }
+            if (hsel == 1) tmem_st4(tacc + kColP + 60, zero6);
             tmem_st_wait();
             signal_drained();                                             // P_h complete (tensor memory), S_h consumed
             TR(0, 15);
@@ -826,6 +817,9 @@ __global__ void __launch_bounds__(kThreads, 2) encoder_tc_kernel(const TcParams 
 
   tc_fence_before();
   __syncthreads();
+#ifdef UITK_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 1024) { g_trace[2][blockIdx.x * 4 + 1] = globaltimer_ns(); g_trace[2][blockIdx.x * 4 + 3] += clock64(); }
+#endif
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);
@@ -838,7 +832,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int read_encoder_trace(long long* host_out, int which, int n) {
 #ifdef UITK_TRACE
-  if (which < 0 || which > 1 || n < 0 || n > 4096) return UITK_EINVAL;
+  if (which < 0 || which > 2 || n < 0 || n > 4096) return UITK_EINVAL;
   UITK_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(long long), (size_t)which * 4096 * sizeof(long long)));
   return UITK_OK;
 #else
@@ -893,7 +887,10 @@ int run_encoder_tc(const EncoderArgs& a) {
   int dev = 0, sms = 0;
   UITK_CHECK_CUDA(cudaGetDevice(&dev));
   UITK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int resident = 2 * sms;                 // two CTAs per SM
+  int resident = 2 * sms;                       // two CTAs per SM
+#ifdef UITK_TRACE
+  if (const char* e = getenv("UITK_TC_GRID")) resident = atoi(e);      // profiling builds only: e.g. 148 = one CTA per SM
+#endif
   const int grid = p.num_tiles < resident ? p.num_tiles : resident;
   if (t_n == 6) {
     UITK_CHECK_CUDA(cudaFuncSetAttribute(encoder_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
