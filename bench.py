@@ -450,9 +450,11 @@ def run_b200(args):
     e2e_steps = max(3, min(steps, 30 if kind == "clips" else 5))
     x_host = x.cpu().pin_memory()
     h2d_floor = None
+    e2e_pipelined = False
     if kind == "clips":
         pipe = HostPipeline(model, B, 16000, chunk=args.chunk)
         run_e2e = lambda: pipe(x_host)
+        e2e_pipelined = True           # timed through submit() / result(): two host batches in flight
     elif kind == "frontend":
         x = None
         torch.cuda.empty_cache()
@@ -473,16 +475,42 @@ def run_b200(args):
                 scores_host.copy_(model.forward_sliding(xs, hop=hop), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return scores_host
+    def e2e_loop(p, src, n):
+        """n batches through the host pipeline, two in flight: every batch is uploaded from pinned host memory and its scores
+        are read back to the host inside the loop (result() blocks until the batch's last download has landed)."""
+        prev, out = None, None
+        for _ in range(n):
+            t = p.submit(src)
+            if prev is not None:
+                out = p.result(prev)
+            prev = t
+        return p.result(prev)
+
     for _ in range(2):
         out_host = run_e2e()
     barrier()
     e2, e3 = ev(), ev()
     e2.record()
-    for _ in range(e2e_steps):
-        out_host = run_e2e()
+    if e2e_pipelined:
+        out_host = e2e_loop(pipe, x_host, e2e_steps)
+    else:
+        for _ in range(e2e_steps):
+            out_host = run_e2e()
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e_sync = None
+    if e2e_pipelined:                 # the one-batch-at-a-time call for comparison (the tail of every batch is exposed)
+        barrier()
+        e8, e9 = ev(), ev()
+        e8.record()
+        for _ in range(e2e_steps):
+            out_host = run_e2e()
+        e9.record()
+        barrier()
+        ms_sync = max_over_ranks(e8.elapsed_time(e9))
+        e2e_sync = {"value": total * e2e_steps / (ms_sync * 1e-3), "ms_per_step": ms_sync / e2e_steps,
+                    "note": "pipe(x_host): one batch at a time, host-synchronous"}
     e2e_value = total * e2e_steps / (ms_e2e * 1e-3)
     e2e_ok = bool(torch.equal(out_host.to(dev), last_local[0])) if kind in ("clips", "sliding") else None
     # the host link's floor: bare pinned H2D of the same bytes on every rank at once (explains e2e scaling: all GPUs of the
@@ -511,8 +539,7 @@ def run_b200(args):
         barrier()
         e6, e7 = ev(), ev()
         e6.record()
-        for _ in range(e2e_steps):
-            pipe16(pcm_host)
+        e2e_loop(pipe16, pcm_host, e2e_steps)
         e7.record()
         barrier()
         ms16 = max_over_ranks(e6.elapsed_time(e7))
@@ -534,6 +561,9 @@ def run_b200(args):
         "data": "synthetic", "config": workload_config(args, arch, world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "chunk": pipe.chunk, "matches_device_path": e2e_ok,
+                "api": ("HostPipeline.submit / result, two host batches in flight (every batch: H2D from pinned host memory, "
+                        "scores D2H and read on the host)") if e2e_pipelined else "host-synchronous call per step",
+                "host_synchronous": e2e_sync,
                 "h2d_floor_gbs_per_gpu": h2d_floor,
                 "h2d_floor_note": f"bare pinned-host->device copy, all {world} rank(s) at once; the e2e step moves "
                                   f"{pipe.h2d_bytes / 1e6:.0f} MB in = {pipe.h2d_bytes / 1e6 / max(h2d_floor, 1e-9):.2f} ms at that rate"},

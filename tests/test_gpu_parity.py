@@ -278,6 +278,36 @@ def test_host_pipeline_matches_device_path_and_handles_q2():
         pipe(torch.zeros(301, 16000).pin_memory())
 
 
+def test_host_pipeline_two_batches_in_flight():
+    """submit / result with two host batches in flight (the uploads of batch i+1 queue behind those of batch i): every batch
+    still equals model(x) bit for bit, in submission order, including a batch that needs the exact re-run (Q2) while its
+    neighbours do not; a third submit without a result is refused."""
+    from uit_mobile_b200.pipeline import HostPipeline
+    m = model("uit_xxs", "trained", "bf16")
+    pipe = HostPipeline(m, 120, 16000, chunk=25, depth=2)
+    batches = [torch.from_numpy(H.noise_clips(120, seed=41)), torch.from_numpy(H.noise_clips(77, seed=42, amp=0.3)),
+               torch.from_numpy(np.concatenate([H.noise_clips(40, seed=43, amp=1e-3), H.adversarial_batch()])),
+               torch.from_numpy(H.noise_clips(5, seed=44))]
+    want = [m(b.to(DEV)).cpu() for b in batches]
+    pinned = [b.pin_memory() for b in batches]
+    got, prev = [], None
+    for x in pinned:
+        t = pipe.submit(x)
+        if prev is not None:
+            got.append(pipe.result(prev).clone())
+        prev = t
+    got.append(pipe.result(prev).clone())
+    assert pipe.respeculated == 1
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+    t0, t1 = pipe.submit(pinned[0]), pipe.submit(pinned[1])
+    with pytest.raises(RuntimeError):
+        pipe.submit(pinned[3])
+    assert torch.equal(pipe.result(t0), want[0]) and torch.equal(pipe.result(t1), want[1])
+    with pytest.raises(RuntimeError):
+        pipe.result(t1)
+
+
 def test_infer_cli_runs_like_inference_py(tmp_path):
     """infer.py (counterpart of the reference's inference.py) on two of the reference's sample clips, random-init weights."""
     import subprocess, sys

@@ -32,15 +32,26 @@ def _bits_to_db(bits: int) -> float:
 
 
 class HostPipeline:
+    """``pipe(wav_host)`` is the synchronous call (host scores back when it returns).  ``submit`` / ``result`` keep up to
+    ``depth`` batches in flight: the uploads of batch i+1 queue right behind those of batch i, so the encoder tail, the score
+    download and the host-side check of batch i run under the H2D of batch i+1 and the PCIe link never idles:
+
+        t = pipe.submit(wav_host)    # pinned host [B, L]; must stay unchanged until result(t)
+        ...                          # submit the next batch before asking for this one
+        y = pipe.result(t)           # pinned host [B, outputdim]; valid until `depth` more batches were submitted
+    """
+
     def __init__(self, model, max_batch: int, L: int = 16000, chunk: int = 1024, device: Optional[torch.device] = None,
-                 speculative: bool = True, dtype: torch.dtype = torch.float32):
+                 speculative: bool = True, dtype: torch.dtype = torch.float32, depth: int = 2):
         self.model = model
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise N.UitkError("HostPipeline needs the model on a CUDA device (no CPU fallback)")
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
         T0 = int(N.lib().uitk_num_frames(L))
         tile = model.tile_clips(T0)                      # tile-aligned chunks keep the result bit-identical to one launch
-        self.max_batch, self.L = max_batch, L
+        self.max_batch, self.L, self.depth = max_batch, L, depth
         self.chunk = max(tile, min(chunk, max_batch) // tile * tile)
         self.speculative = speculative
         T = int(N.lib().uitk_num_frames(L))
@@ -49,21 +60,37 @@ class HostPipeline:
             raise ValueError("dtype must be float32 (reference contract) or int16 (PCM ingest, x = pcm / 32768)")
         self.dtype = dtype
         self.stage = [torch.empty((self.chunk, L), dtype=dtype, device=dev) for _ in range(2)]
-        self.db = torch.empty((max_batch, 64, T), dtype=torch.float32, device=dev)
-        self.words = torch.zeros(2, dtype=torch.int32, device=dev)          # [max power bits, min power bits]
-        self.probs = torch.empty((max_batch, model.outputdim), dtype=torch.float32, device=dev)
-        self.out_host = torch.empty((max_batch, model.outputdim), dtype=torch.float32).pin_memory()
-        self.words_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._free = [None, None]                      # compute-done events per staging buffer (carried across batches)
+        self._n_chunks = 0
+        self._slots = [None] * depth                   # per-batch buffers, allocated on first use
+        self._T = T
         self.words_init = torch.tensor([0, _INF_BITS], dtype=torch.int32, device=dev)
         self.copy_stream = torch.cuda.Stream(dev)
         self.d2h_stream = torch.cuda.Stream(dev)       # PCIe is full duplex: scores of chunk i go back under the H2D of chunk i+2
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.respeculated = 0          # how many calls needed the exact re-run
+        self._next = 0
+        for i in range(depth):
+            self._slot(i)
+        torch.cuda.current_stream(dev).synchronize()   # buffers were allocated on the caller's stream: order the side streams once
+
+    def _slot(self, i: int):
+        if self._slots[i] is None:
+            dev, m = self.device, self.model
+            self._slots[i] = {
+                "db": torch.empty((self.max_batch, 64, self._T), dtype=torch.float32, device=dev),
+                "words": torch.zeros(2, dtype=torch.int32, device=dev),            # [max power bits, min power bits]
+                "probs": torch.empty((self.max_batch, m.outputdim), dtype=torch.float32, device=dev),
+                "out_host": torch.empty((self.max_batch, m.outputdim), dtype=torch.float32).pin_memory(),
+                "words_host": torch.zeros(2, dtype=torch.int32).pin_memory(),
+                "ticket": None,
+            }
+        return self._slots[i]
 
     @torch.no_grad()
-    def __call__(self, wav_host: torch.Tensor) -> torch.Tensor:
-        """wav_host: pinned float32 [B, L] host tensor.  Returns a pinned host view [B, outputdim]."""
+    def submit(self, wav_host: torch.Tensor) -> int:
+        """Queue one batch (pinned host [B, L]); returns a ticket for ``result``.  No host synchronisation."""
         if wav_host.is_cuda or wav_host.dtype != self.dtype or wav_host.dim() != 2 or wav_host.shape[1] != self.L:
             raise ValueError(f"expected a host {self.dtype} [B, {self.L}] tensor")
         B = wav_host.shape[0]
@@ -72,17 +99,27 @@ class HostPipeline:
         m = self.model
         if m.training:
             raise NotImplementedError("inference only: call model.eval()")
+        ticket = self._next
+        self._next += 1
+        S = self._slot(ticket % self.depth)
+        if S["ticket"] is not None:
+            raise RuntimeError(f"batch {S['ticket']} is still pending: call result() before submitting {self.depth} more batches")
         main = torch.cuda.current_stream(self.device)
-        self.words.copy_(self.words_init)
-        max_w, min_w = self.words[0:1], self.words[1:2]
-        self.copy_stream.wait_stream(main)
+        words = S["words"]
+        words.copy_(self.words_init)
+        max_w, min_w = words[0:1], words[1:2]
         sharded = m.process_group is not None
+        # (no stream-wide waits here: the staging buffers are guarded by their own events and the slot's previous download was
+        # consumed by result(), so the uploads of this batch queue right behind those of the previous one)
         # Sharded: the top-dB scope is the GLOBAL batch.  Speculation stays on (tensor-core configuration): every chunk is encoded
-        # with this rank's running maximum, ONE all-reduce(MAX) of the word follows the last chunk, and the host check below
-        # compares this rank's minimum with the global cutoff.
+        # with this rank's running maximum, ONE all-reduce(MAX) of the word follows the last chunk, and the host check in
+        # result() compares this rank's minimum with the global cutoff.
         spec = self.speculative and (not sharded or m._cfg().tensor_core)
-        free = [None, None]                           # compute-done events per staging buffer
-        for i, b0 in enumerate(range(0, B, self.chunk)):
+        free = self._free
+        db, probs, out_host = S["db"], S["probs"], S["out_host"]
+        for b0 in range(0, B, self.chunk):
+            i = self._n_chunks
+            self._n_chunks += 1
             nb = min(self.chunk, B - b0)
             buf = self.stage[i & 1][:nb]
             with torch.cuda.stream(self.copy_stream):
@@ -92,41 +129,62 @@ class HostPipeline:
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
-            db_i = self.db[b0:b0 + nb]
+            db_i = db[b0:b0 + nb]
             m.front_end.logmel_unclamped(buf, out=db_i, max_pow=max_w, min_pow=min_w)
             done = torch.cuda.Event()
             done.record(main)
             free[i & 1] = done
             if spec:
-                m.encode(db_i, max_w, out=self.probs[b0:b0 + nb])
+                m.encode(db_i, max_w, out=probs[b0:b0 + nb])
                 scored = torch.cuda.Event()
                 scored.record(main)
                 with torch.cuda.stream(self.d2h_stream):
                     self.d2h_stream.wait_event(scored)
-                    self.out_host[b0:b0 + nb].copy_(self.probs[b0:b0 + nb], non_blocking=True)
-        final = self.words                             # [final max, this rank's min]
+                    out_host[b0:b0 + nb].copy_(probs[b0:b0 + nb], non_blocking=True)
+        final = words                                  # [final max, this rank's min]
         if sharded:
-            final = self.words.clone()
+            final = words.clone()
             torch.distributed.all_reduce(final[0:1], op=torch.distributed.ReduceOp.MAX, group=m.process_group)
         if not spec:
-            m.encode(self.db[:B], final[0:1], out=self.probs[:B])
-        out = self.out_host[:B]
-        if not spec:
-            out.copy_(self.probs[:B], non_blocking=True)
-        self.words_host.copy_(final, non_blocking=True)
-        main.synchronize()
-        self.d2h_stream.synchronize()
-        if spec:
-            mx, mn = int(self.words_host[0]), int(self.words_host[1])
+            m.encode(db[:B], final[0:1], out=probs[:B])
+        tail = torch.cuda.Event()
+        tail.record(main)
+        with torch.cuda.stream(self.d2h_stream):       # the last bytes of the batch: (exact-path scores,) the two words
+            self.d2h_stream.wait_event(tail)
+            if not spec:
+                out_host[:B].copy_(probs[:B], non_blocking=True)
+            S["words_host"].copy_(final, non_blocking=True)
+            finished = torch.cuda.Event()
+            finished.record(self.d2h_stream)
+        S.update(ticket=ticket, B=B, spec=spec, final=final, finished=finished)
+        self.h2d_bytes = B * self.L * wav_host.element_size()
+        self.d2h_bytes = B * m.outputdim * 4 + 8
+        return ticket
+
+    @torch.no_grad()
+    def result(self, ticket: int) -> torch.Tensor:
+        """Host scores [B, outputdim] (pinned view) of a submitted batch; blocks until its last download has landed."""
+        S = self._slots[ticket % self.depth]
+        if S is None or S["ticket"] != ticket:
+            raise RuntimeError(f"unknown or already collected ticket {ticket}")
+        S["finished"].synchronize()
+        B, m = S["B"], self.model
+        out = S["out_host"][:B]
+        if S["spec"]:
+            mx, mn = int(S["words_host"][0]), int(S["words_host"][1])
             if B and _bits_to_db(mn) < _bits_to_db(mx) - 120.0 + 1e-3:      # conservative margin vs the device's log2-based dB
                 # some value lies below the final cutoff: redo the encoder with the final batch maximum (exact path)
                 self.respeculated += 1
-                m.encode(self.db[:B], final[0:1], out=self.probs[:B])
-                out.copy_(self.probs[:B], non_blocking=True)
+                main = torch.cuda.current_stream(self.device)
+                m.encode(S["db"][:B], S["final"][0:1], out=S["probs"][:B])
+                out.copy_(S["probs"][:B], non_blocking=True)
                 main.synchronize()
-        self.h2d_bytes = B * self.L * wav_host.element_size()
-        self.d2h_bytes = B * m.outputdim * 4 + 8
+        S["ticket"] = None
         return out
+
+    def __call__(self, wav_host: torch.Tensor) -> torch.Tensor:
+        """wav_host: pinned float32 [B, L] host tensor.  Returns a pinned host view [B, outputdim]."""
+        return self.result(self.submit(wav_host))
 
 
 class FrontEndHostPipeline:
