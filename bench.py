@@ -266,8 +266,16 @@ def run_b200(args):
 
     torch.manual_seed(0)                                        # identical random-init weights on every rank
     model = getattr(U.models, arch)(outputdim=537, target_length=102, precision=args.precision).to(dev).eval()
+    max_exchange = None
     if world > 1 and args.diag != "nogroup":
         model.process_group = dist.group.WORLD
+        max_exchange = "nccl all_reduce(MAX) of one word, async under the speculative encode"
+        if not args.nccl_gather:
+            try:
+                model.peer_words = sharding.PeerWords(dist.group.WORLD, dev)
+                max_exchange = "PeerWords: publish / collect kernels over NVLink peer memory (no NCCL call in the step)"
+            except Exception as e:                    # no peer mapping on this box: NCCL
+                max_exchange += f" (PeerWords unavailable: {type(e).__name__}: {str(e)[:100]})"
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     def barrier():
@@ -570,7 +578,7 @@ def run_b200(args):
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms,
         "timed_region": ("BatchPipeline: two batches in flight (front-end of step i+1 under the encoder tail of step i)" if pipelined
                          else "launches serialised on one stream"),
-        "sequential": sequential, "score_gather": peer[1] if world > 1 else None, **({"diag_INVALID_AS_BENCH": args.diag} if args.diag else {}),
+        "sequential": sequential, "score_gather": peer[1] if world > 1 else None, "max_word_exchange": max_exchange, **({"diag_INVALID_AS_BENCH": args.diag} if args.diag else {}),
     }
     if e2e16:
         line["e2e_int16_pcm"] = e2e16

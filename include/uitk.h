@@ -30,7 +30,7 @@ extern "C" {
 #define UITK_API
 #endif
 
-#define UITK_VERSION 220
+#define UITK_VERSION 230
 
 #define UITK_OK 0
 #define UITK_EINVAL (-1)    /* bad shape / argument */
@@ -168,6 +168,20 @@ UITK_API int uitk_encoder(const uitk_encoder_cfg* cfg, const void* d_encoder_blo
 UITK_API int uitk_encoder_fixup(const uitk_encoder_cfg* cfg, const void* d_encoder_blob, const float* d_db, int64_t B, int64_t T,
                        int target_length, int eval_avg, const uint32_t* d_max_pow, const uint32_t* d_max_used,
                        const uint32_t* d_min_pow, float* d_probs, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the batch-global top-dB scope (Q2) across the GPUs of one box, without a collective library call -----------------
+ * Replaces `torch.distributed.all_reduce(max_pow, MAX)` (what a sharded caller of models/uit.py:455-462 needs so that
+ * AmplitudeToDB's cutoff spans the global batch).  Every rank owns a slot of uitk_peer_words_slot_bytes() bytes (zeroed once)
+ * that all peers have mapped (NVLink peer memory: CUDA IPC / torch symmetric memory);
+ *   uitk_peer_words_publish: stores *d_word and then `epoch` (release, system scope) into this rank's slot        - 1 thread
+ *   uitk_peer_words_collect: waits until the slot of every rank shows `epoch`, writes the MAX of the words        - 1 warp
+ * d_peer_slots is a DEVICE array of n_ranks pointers (own slot included).  Epochs count 1, 2, 3, ... and every rank must call
+ * publish(e) and collect(e) in this order on one stream for every e (the ring holds 4 epochs: a rank can be at most one epoch
+ * ahead of a peer that still has to read).  The collect kernel spins on peer memory: launch it where the wait is short (after
+ * the speculative uitk_encoder, before uitk_encoder_fixup). */
+UITK_API size_t uitk_peer_words_slot_bytes(void);
+UITK_API int uitk_peer_words_publish(uint32_t* d_my_slot, const uint32_t* d_word, uint32_t epoch, void* stream);
+UITK_API int uitk_peer_words_collect(const uint32_t* const* d_peer_slots, int n_ranks, uint32_t epoch, uint32_t* d_word_out, void* stream);
 
 /* ---- forward_features / forward_head (models/uit.py:379-412) as separate entry points -----------------------------
  * The reference exposes both methods; uitk_encoder fuses them.  These two keep the method-level contract:

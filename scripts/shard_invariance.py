@@ -42,6 +42,22 @@ try:
         out, done = pg(bp.result(t))
         torch.cuda.current_stream().wait_event(done)
         ok = ok and torch.equal(ref, out)
+    # the batch-maximum word through NVLink peer memory (sharding.PeerWords) instead of the NCCL all-reduce: plain forward,
+    # several steps (epoch ring), and through BatchPipeline.  The silent clip sits on rank 0, the loudest on the last rank, so
+    # the conditional exact re-run really fires on rank 0.
+    model.peer_words = sharding.PeerWords(dist.group.WORLD, dev)
+    for rep in range(6):
+        with torch.no_grad():
+            out, done = pg(model(xl))
+        torch.cuda.current_stream().wait_event(done)
+        ok = ok and torch.equal(ref, out)
+    t0 = bp.submit(xl); t1 = bp.submit(xl)
+    for t in (t0, t1):
+        out, done = pg(bp.result(t))
+        torch.cuda.current_stream().wait_event(done)
+        ok = ok and torch.equal(ref, out)
+    model.peer_words = None
+    peer_note += " + PeerWords"
 except Exception as exc:                                   # no peer mapping on this box
     peer_note = f"PeerGather unavailable ({type(exc).__name__}: {str(exc)[:100]})"
 t = torch.tensor([int(ok)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -68,7 +68,7 @@ def assert_logmel_close(got, x, ref32):
 
 def test_library_loaded_is_in_tree():
     from uit_mobile_b200 import _native as N
-    assert N.lib().uitk_version() == 220
+    assert N.lib().uitk_version() == 230
     assert N.LIB_PATH.endswith("uit_mobile_b200/libuitk.so")
 
 

@@ -134,6 +134,18 @@ def test_sharded_forward_world1_nccl_and_empty_shard():
             got = m.forward_sliding(stream, hop=1600)
             m.process_group = None
             assert torch.equal(got, m.forward_sliding(stream, hop=1600))
+        # the same with the maximum word exchanged through peer memory (sharding.PeerWords) instead of the NCCL all-reduce:
+        # ten steps (the epoch ring wraps), an empty shard in between
+        from uit_mobile_b200 import sharding
+        m = _uit("uit_xxxs", "trained", "bf16")
+        want = m(x)
+        m.process_group = dist.group.WORLD
+        m.peer_words = sharding.PeerWords(dist.group.WORLD, torch.device(DEV))
+        for i in range(10):
+            assert torch.equal(m(x), want)
+            if i == 4:
+                assert tuple(m(torch.zeros(0, 16000, device=DEV)).shape) == (0, 537)
+        assert m.peer_words.epoch == 11
         torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.uitk_version() == 220
+    assert lib.uitk_version() == 230
 
 
 def test_geometry_helpers_match_oracle(lib):

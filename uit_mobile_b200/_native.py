@@ -65,6 +65,9 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uitk_encoder_fixup": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uitk_peer_words_slot_bytes": (C.c_size_t, []),
+    "uitk_peer_words_publish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "uitk_peer_words_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]),
     "uitk_init_bn": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "uitk_forward_features_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderCfg), C.c_int64, C.c_int64]),
     "uitk_forward_features": (C.c_int, [C.POINTER(EncoderCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,

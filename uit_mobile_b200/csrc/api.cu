@@ -57,6 +57,27 @@ int uitk_logmel_i16(const int16_t* d_pcm, int64_t B, int64_t L, int64_t ld_pcm, 
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t uitk_peer_words_slot_bytes(void) { return peer_words_slot_bytes(); }
+
+int uitk_peer_words_publish(uint32_t* d_my_slot, const uint32_t* d_word, uint32_t epoch, void* stream) {
+  UITK_REQUIRE(d_my_slot && d_word, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(epoch != 0, UITK_EINVAL, "epochs start at 1 (a zeroed slot must not look published)");
+  UITK_REQUIRE(aligned(d_my_slot, 16) && aligned(d_word, 4), UITK_EALIGN, "misaligned pointer");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return launch_words_publish(d_my_slot, d_word, epoch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int uitk_peer_words_collect(const uint32_t* const* d_peer_slots, int n_ranks, uint32_t epoch, uint32_t* d_word_out, void* stream) {
+  UITK_REQUIRE(d_peer_slots && d_word_out, UITK_EINVAL, "null pointer");
+  UITK_REQUIRE(n_ranks >= 1 && n_ranks <= 1024, UITK_EINVAL, "rank count %d out of range", n_ranks);
+  UITK_REQUIRE(epoch != 0, UITK_EINVAL, "epochs start at 1");
+  UITK_REQUIRE(aligned(d_peer_slots, 8) && aligned(d_word_out, 4), UITK_EALIGN, "misaligned pointer");
+  int rc = check_arch();
+  if (rc != UITK_OK) return rc;
+  return launch_words_collect(d_peer_slots, n_ranks, epoch, d_word_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 size_t uitk_logmel_sliding_workspace_bytes(int64_t n_samples) {
   return n_samples < 0 ? 0 : (size_t)64 * (size_t)(1 + n_samples / UITK_HOP) * sizeof(float);
 }

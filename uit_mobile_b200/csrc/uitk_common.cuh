@@ -169,6 +169,9 @@ int run_encoder_fp32(const EncoderArgs& a);
 int run_encoder_tc(const EncoderArgs& a);
 int read_encoder_trace(long long* host_out, int which, int n);
 int run_umma_selftest(const float* A, const void* Bp, const float* Cinit, float* C, int N, int K, int a_in_tmem, cudaStream_t s);
+size_t peer_words_slot_bytes();
+int launch_words_publish(uint32_t* my_slot, const uint32_t* word, uint32_t epoch, cudaStream_t s);
+int launch_words_collect(const uint32_t* const* peer_slots, int n, uint32_t epoch, uint32_t* out, cudaStream_t s);
 size_t encoder_tc_bf16_section_bytes(int depth);
 size_t encoder_tc_block_bytes();
 size_t encoder_tc_workspace_bytes(int64_t clip_crops, int64_t rows);

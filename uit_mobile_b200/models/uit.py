@@ -314,6 +314,7 @@ class UITBase(nn.Module):
         self.depth, self.num_heads, self.mlp_ratio = depth, num_heads, mlp_ratio
         self.precision = precision
         self.process_group = process_group          # batch-sharded inference: all-reduce(max) of the top-dB scope
+        self.peer_words = None                      # optional sharding.PeerWords: the same exchange through NVLink peer memory
         self.max_clips_per_launch = 16384
 
         # Everything the kernels do not implement is refused up front (no silent fallback).
@@ -543,13 +544,26 @@ class UITBase(nn.Module):
             dist.all_reduce(max_w, op=dist.ReduceOp.MAX, group=self.process_group)
             return self.encode(db, max_w, out=out)
         # Sharded, tensor-core configuration: NO collective on the critical path.  Encode speculatively with the rank-local
-        # maximum while the all-reduce(MAX) of [max, -1 - min] (non-negative floats order like their int32 bit patterns) runs on
-        # the NCCL stream, then launch the device-conditional exact re-run: its kernels return at once unless this rank's
-        # cutoff was below the global one AND one of its values lies under the global cutoff (uitk_encoder_fixup).
+        # maximum, learn the global maximum meanwhile, then launch the device-conditional exact re-run: its kernels return at
+        # once unless this rank's cutoff was below the global one AND one of its values lies under the global cutoff
+        # (uitk_encoder_fixup).
+        blob = self._encoder_blob(db.device) if db.shape[0] else None
+        empty = torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
+        pw = getattr(self, "peer_words", None)
+        if pw is not None:
+            # global maximum through NVLink peer memory (sharding.PeerWords): publish now, read the peers' words after the
+            # speculative encode (they are long there by then) - no NCCL kernel, no collective launch
+            epoch = pw.publish(max_w)
+            probs = self.encode(db, max_w, out=out, _blob=blob) if db.shape[0] else empty
+            g = pw.collect(epoch, torch.empty(1, dtype=torch.int32, device=db.device))
+            if db.shape[0]:
+                self.encode(db, g, out=probs, fixup=(max_w, min_w), _blob=blob)
+            return probs
+        # NCCL: the all-reduce(MAX) of [max, -1 - min] (non-negative floats order like their int32 bit patterns) runs on the
+        # NCCL stream under the speculative encode
         g = torch.bitwise_xor(words, self._words_mask(db.device))      # [max, ~min] = [max, -1 - min]: ONE MAX all-reduce for both
         work = dist.all_reduce(g, op=dist.ReduceOp.MAX, group=self.process_group, async_op=True)
-        blob = self._encoder_blob(db.device) if db.shape[0] else None
-        probs = self.encode(db, max_w, out=out, _blob=blob) if db.shape[0] else torch.empty((0, self.outputdim), dtype=torch.float32, device=db.device)
+        probs = self.encode(db, max_w, out=out, _blob=blob) if db.shape[0] else empty
         work.wait()
         if db.shape[0]:
             self.encode(db, g[0:1], out=probs, fixup=(max_w, min_w), _blob=blob)

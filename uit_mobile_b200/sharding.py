@@ -76,6 +76,53 @@ def sharded_forward(model, wav_local: torch.Tensor, total: int, group=None, gath
     return gather_scores(local, total, group, align) if gather else local
 
 
+class PeerWords:
+    """The batch-maximum word of every rank, exchanged through NVLink peer memory instead of ``all_reduce(MAX)``.
+
+    Every rank owns a 64-byte slot in a symmetric-memory allocation (mapped by all peers once, at construction); per step the
+    rank PUBLISHES its word there (one 1-thread kernel: word, then an epoch counter with release semantics) and later COLLECTS
+    the maximum over all ranks (one 1-warp kernel that reads the peers' slots with system-scope loads, waiting for their epoch).
+    No NCCL kernel, no collective launch on the host: an NCCL kernel needs a CTA slot the persistent encoder does not leave
+    until its last tile wave, and costs ~40 us of host time per enqueue.
+
+        model.peer_words = PeerWords(group, device)      # next to model.process_group; UITBase._finish uses it when present
+
+    Every rank must run the same sequence of steps (publish and collect are collective in the same sense all_reduce is)."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        n = int(N.lib().uitk_peer_words_slot_bytes()) // 4
+        self.slot = symm.empty((n,), dtype=torch.int32, device=self.device)
+        self.slot.zero_()
+        self.hdl = symm.rendezvous(self.slot, group)
+        self.peers = [self.hdl.get_buffer(r, (n,), torch.int32) for r in range(self.world)]
+        self.ptrs = torch.tensor([p.data_ptr() for p in self.peers], dtype=torch.int64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group)                      # every slot is zeroed before anyone publishes or polls
+        self.epoch = 0
+
+    def publish(self, word: torch.Tensor) -> int:
+        """Publish this rank's int32 word (device tensor [1]) on the current stream; returns the epoch to collect with."""
+        from . import _native as N
+        self.epoch += 1
+        if self.epoch >= 1 << 32:
+            self.epoch = 1
+        N.check(N.lib().uitk_peer_words_publish(self.slot.data_ptr(), word.data_ptr(), self.epoch,
+                                                torch.cuda.current_stream(self.device).cuda_stream), "uitk_peer_words_publish")
+        return self.epoch
+
+    def collect(self, epoch: int, out: torch.Tensor) -> torch.Tensor:
+        """MAX of all ranks' words of ``epoch`` into ``out`` (int32 device tensor [1]) on the current stream."""
+        from . import _native as N
+        N.check(N.lib().uitk_peer_words_collect(self.ptrs.data_ptr(), self.world, epoch, out.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream), "uitk_peer_words_collect")
+        return out
+
+
 class PeerGather:
     """All-gather of the per-rank score blocks through NVLink peer memory, moved by the COPY ENGINES.
 
