@@ -271,11 +271,18 @@ def run_b200(args):
         model.process_group = dist.group.WORLD
         max_exchange = "nccl all_reduce(MAX) of one word, async under the speculative encode"
         if not args.nccl_gather:
+            why = ""
             try:
                 model.peer_words = sharding.PeerWords(dist.group.WORLD, dev)
-                max_exchange = "PeerWords: publish / collect kernels over NVLink peer memory (no NCCL call in the step)"
             except Exception as e:                    # no peer mapping on this box: NCCL
-                max_exchange += f" (PeerWords unavailable: {type(e).__name__}: {str(e)[:100]})"
+                why = f"{type(e).__name__}: {str(e)[:100]}"
+            ok = torch.tensor([0 if model.peer_words is None else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)            # every rank takes the same path, or none does
+            if int(ok.item()):
+                max_exchange = "PeerWords: publish / collect kernels over NVLink peer memory (no NCCL call in the step)"
+            else:
+                model.peer_words = None
+                max_exchange += f" (PeerWords unavailable on some rank: {why})"
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     def barrier():
@@ -354,12 +361,19 @@ def run_b200(args):
     equal_shards = len(set(shard_sizes)) == 1
     last_local = [None]
     if world > 1 and kind != "frontend" and not args.nccl_gather:
+        why = ""
         try:
             peer[0] = sharding.PeerGather(shard_sizes, 537, dist.group.WORLD, dev, depth=2)
+        except Exception as e:                        # no peer mapping on this box: NCCL
+            why = f"{type(e).__name__}: {str(e)[:120]}"
+        ok = torch.tensor([0 if peer[0] is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # every rank takes the same path, or none does
+        if int(ok.item()):
             peer[1] = "PeerGather: copy-engine pulls over NVLink peer memory (torch symmetric memory), no SMs"
             equal_shards = True                       # PeerGather takes ragged shards as they are
-        except Exception as e:                        # no peer mapping on this box: NCCL
-            peer[1] = f"nccl all_gather (PeerGather unavailable: {type(e).__name__}: {str(e)[:120]})"
+        else:
+            peer[0] = None
+            peer[1] = f"nccl all_gather (PeerGather unavailable on some rank: {why})"
 
     def step(marks=None):
         with torch.no_grad():
